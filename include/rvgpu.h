@@ -1,0 +1,101 @@
+/*
+ * rvgpu.h -- C ABI of librvgpu.so: the B200 (sm_100a) replacement for the reference's per-evaluation
+ * FFI into librebound.
+ *
+ * What it replaces.  rvel-mcmc reaches native code through ctypes, one call per observation epoch:
+ *   clibrebound.reb_integrate(byref(sim), c_double(tmax))      (rebound/simulation.py, reached from
+ *                                                               state.py:71, state.py:263, state.py:275)
+ * preceded by per-evaluation set-up calls (state.py:37-46: Simulation(), add(), move_to_com()) and
+ * followed by reads of sim.particles[0].vx (state.py:72).  A return value of 3 (REB_EXIT_ENCOUNTER)
+ * becomes the Python exception rebound.Encounter (mcmc.py:119,176).  This library moves the whole
+ * evaluation (set-up, every integrate() hop, the chi^2 sum of state.py:89-98) behind ONE call for a
+ * whole batch of parameter vectors, and reports Encounter / hard-prior / non-finite outcomes as a
+ * per-walker status instead of an exception.
+ *
+ * Conventions: every entry point returns 0 on success or a negative error code (rv_last_error() gives
+ * the message); no exception crosses the ABI; all arrays are C-contiguous float64 / int32 owned by the
+ * caller; the library keeps no host pointer after a call returns.  Element slots of a planet are
+ * ordered m, a, h, k, l, ix, iy (RV_EL_*).
+ */
+#ifndef RVGPU_H
+#define RVGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rv_ctx rv_ctx;     /* one GPU + stream + scratch; one per host thread / rank       */
+typedef struct rv_obs rv_obs;     /* observation set resident in HBM (observations.py:6-16)        */
+typedef struct rv_model rv_model; /* parameter schema resident in HBM (state.py:8-31)              */
+
+/* per-walker status */
+#define RV_OK          0   /* evaluated                                                            */
+#define RV_PRIOR       1   /* State.priorHard() true (state.py:299-315): logp = -inf, no integration */
+#define RV_ENCOUNTER   3   /* rebound.Encounter (REB_EXIT_ENCOUNTER): logp = -inf                  */
+#define RV_NONFINITE   8   /* non-finite state or step-count bound hit                             */
+#define RV_NOT_SPD     9   /* SMALA metric not positive definite (mcmc.py:179-183 quits)           */
+
+/* element slots */
+#define RV_EL_M 0
+#define RV_EL_A 1
+#define RV_EL_H 2
+#define RV_EL_K 3
+#define RV_EL_L 4
+#define RV_EL_IX 5
+#define RV_EL_IY 6
+#define RV_NELEM 7
+#define RV_MAX_PLANETS 3
+
+/* ---- context ---------------------------------------------------------------------------------- */
+int rv_ctx_create(int device, rv_ctx** out);
+int rv_ctx_destroy(rv_ctx* ctx);
+const char* rv_last_error(const rv_ctx* ctx);   /* ctx may be NULL: last creation error           */
+int rv_device_info(const rv_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, int* clock_khz);
+
+/* ---- observations: replaces the Observation container (observations.py:6-16, 52-69) ----------- */
+/* tf/rvf/errf: forward leg in obs.tf order; tb/rvb/errb: backward leg in obs.tb order (ascending, as
+ * the reference integrates it, state.py:91); npoints: the Npoints normaliser of state.py:98.      */
+int rv_obs_create(rv_ctx* ctx, const double* tf, const double* rvf, const double* errf, int nf,
+                  const double* tb, const double* rvb, const double* errb, int nb, double npoints,
+                  rv_obs** out);
+int rv_obs_destroy(rv_obs* obs);
+
+/* ---- model: replaces State's schema (state.py:8-31) + setup_sim constants (state.py:36-47) ---- */
+/* fixed[n_planets][7]: element values used where a slot is not free (absent keys = 0);
+ * free_planet/free_elem[nvars]: slot of each entry of a parameter vector, in State.get_params() order;
+ * hill_factor: State.hillRadiusFactor; dims: 0 auto, 2 coplanar, 3 general.                       */
+int rv_model_create(rv_ctx* ctx, int n_planets, const double* fixed, int nvars, const int32_t* free_planet,
+                    const int32_t* free_elem, double hill_factor, int dims, rv_model** out);
+int rv_model_destroy(rv_model* model);
+/* options: "dt0" (1e-3), "epsilon" (1e-9), "max_attempts", "mapping" (0 lane-per-planet, 1 thread-per-walker) */
+int rv_model_set_option(rv_model* model, const char* key, double value);
+
+/* ---- State.get_logp (state.py:103-110) for W parameter vectors; HOST buffers -------------------- */
+/* theta[W][nvars] -> logp[W], status[W].  Copies in, runs, copies out, synchronises.              */
+int rv_loglik(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, const double* theta, int64_t W,
+              double* logp, int32_t* status);
+
+/* Same with DEVICE buffers, asynchronous on `stream` (a cudaStream_t; NULL = the context's stream). */
+int rv_loglik_dev(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, const double* d_theta, int64_t W,
+                  double* d_logp, int32_t* d_status, void* stream);
+
+/* ---- State.get_rv (state.py:61-73): star vx at times[nt] (visited in the given order) ---------- */
+/* rv[W][nt]; status[W]; no prior test (as the reference).  HOST buffers.                          */
+int rv_rv_curve(rv_ctx* ctx, const rv_model* model, const double* theta, int64_t W, const double* times,
+                int nt, double* rv, int32_t* status);
+
+/* ---- work accounting: force evaluations and IAS15 step attempts since the last reset ----------- */
+int rv_work_counters(rv_ctx* ctx, uint64_t out[2], int reset);
+int rv_count_work(rv_ctx* ctx, int enable);     /* off by default (atomics per item when on)       */
+
+/* ---- FP64 FMA-pipe peak of this GPU (TFLOP/s), the roofline denominator ------------------------ */
+int rv_fp64_peak(rv_ctx* ctx, double* tflops);
+
+int rv_sync(rv_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RVGPU_H */

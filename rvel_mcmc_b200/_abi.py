@@ -1,0 +1,221 @@
+"""ctypes binding of librvgpu.so (include/rvgpu.h).
+
+This is the analogue of rebound's own ctypes layer (``clibrebound.reb_integrate(byref(sim), c_double(tmax))``
+reached from state.py:71): one thin call per *batch* of parameter vectors instead of one per epoch.
+"""
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+RV_OK, RV_PRIOR, RV_ENCOUNTER, RV_NONFINITE, RV_NOT_SPD = 0, 1, 3, 8, 9
+ELEMS = ("m", "a", "h", "k", "l", "ix", "iy")       # ABI slot order (RV_EL_*)
+MAX_PLANETS = 3
+
+
+class RvGpuError(RuntimeError):
+    """The CUDA library is missing or a call into it failed (there is no CPU fallback)."""
+
+
+class Encounter(Exception):
+    """Two bodies came closer than exit_min_distance (mirrors rebound.Encounter; mcmc.py:119,176)."""
+
+
+def lib_path():
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "librvgpu.so")
+
+
+_lib = None
+_lib_lock = threading.Lock()
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+
+_SIGNATURES = {
+    "rv_ctx_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "rv_ctx_destroy": (C.c_int, [C.c_void_p]),
+    "rv_last_error": (C.c_char_p, [C.c_void_p]),
+    "rv_device_info": (C.c_int, [C.c_void_p, _ip, _ip, _ip, _ip]),
+    "rv_obs_create": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                C.c_void_p, C.c_int, C.c_double, C.POINTER(C.c_void_p)]),
+    "rv_obs_destroy": (C.c_int, [C.c_void_p]),
+    "rv_model_create": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_double,
+                                  C.c_int, C.POINTER(C.c_void_p)]),
+    "rv_model_destroy": (C.c_int, [C.c_void_p]),
+    "rv_model_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_double]),
+    "rv_loglik": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "rv_loglik_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                C.c_void_p]),
+    "rv_rv_curve": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p,
+                              C.c_void_p]),
+    "rv_work_counters": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.c_int]),
+    "rv_count_work": (C.c_int, [C.c_void_p, C.c_int]),
+    "rv_fp64_peak": (C.c_int, [C.c_void_p, _dp]),
+    "rv_sync": (C.c_int, [C.c_void_p]),
+}
+
+
+def exported_symbols():
+    """Every entry point include/rvgpu.h declares (used by the CPU-side load test)."""
+    return sorted(_SIGNATURES)
+
+
+def load():
+    """Load librvgpu.so; raises RvGpuError if it has not been built (no fallback)."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        path = lib_path()
+        if not os.path.exists(path):
+            raise RvGpuError("%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                             "(rvel_mcmc_b200 has no CPU fallback)" % path)
+        lib = C.CDLL(path)
+        for name, (res, args) in _SIGNATURES.items():
+            try:
+                fn = getattr(lib, name)
+            except AttributeError:
+                continue          # optional entry points are checked where they are used
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+        return lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class Context(object):
+    """One GPU (rv_ctx).  Calls are synchronous; one Context per host thread / rank."""
+
+    def __init__(self, device=0):
+        self.lib = load()
+        h = C.c_void_p()
+        rc = self.lib.rv_ctx_create(int(device), C.byref(h))
+        if rc != 0:
+            raise RvGpuError("rv_ctx_create failed (%d): %s" % (rc, self.lib.rv_last_error(None).decode()))
+        self.h = h
+        self.device = int(device)
+        self._models = {}
+
+    def check(self, rc, what):
+        if rc != 0:
+            raise RvGpuError("%s failed (%d): %s" % (what, rc, self.lib.rv_last_error(self.h).decode()))
+
+    def device_info(self):
+        v = [C.c_int32() for _ in range(4)]
+        self.check(self.lib.rv_device_info(self.h, *[C.byref(x) for x in v]), "rv_device_info")
+        return dict(sm_count=v[0].value, cc=(v[1].value, v[2].value), clock_khz=v[3].value)
+
+    def fp64_peak_tflops(self):
+        out = C.c_double()
+        self.check(self.lib.rv_fp64_peak(self.h, C.byref(out)), "rv_fp64_peak")
+        return out.value
+
+    def count_work(self, enable=True):
+        self.check(self.lib.rv_count_work(self.h, 1 if enable else 0), "rv_count_work")
+
+    def work_counters(self, reset=False):
+        out = (C.c_uint64 * 2)()
+        self.check(self.lib.rv_work_counters(self.h, out, 1 if reset else 0), "rv_work_counters")
+        return int(out[0]), int(out[1])
+
+    def sync(self):
+        self.check(self.lib.rv_sync(self.h), "rv_sync")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.rv_ctx_destroy(self.h)
+            self.h = None
+
+
+class ObsHandle(object):
+    """Observation arrays resident in HBM (rv_obs)."""
+
+    def __init__(self, ctx, tf, rvf, errf, tb, rvb, errb, npoints):
+        self.ctx = ctx
+        tf, rvf, errf, tb, rvb, errb = [_f64(x) for x in (tf, rvf, errf, tb, rvb, errb)]
+        if not (len(tf) == len(rvf) == len(errf) and len(tb) == len(rvb) == len(errb)):
+            raise ValueError("observation arrays of one leg must have equal lengths")
+        self.nf, self.nb, self.npoints = len(tf), len(tb), float(npoints)
+        h = C.c_void_p()
+        ctx.check(ctx.lib.rv_obs_create(ctx.h, _ptr(tf), _ptr(rvf), _ptr(errf), len(tf), _ptr(tb), _ptr(rvb),
+                                        _ptr(errb), len(tb), float(npoints), C.byref(h)), "rv_obs_create")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.ctx.lib.rv_obs_destroy(self.h)
+            self.h = None
+
+
+class ModelHandle(object):
+    """Parameter schema resident in HBM (rv_model)."""
+
+    def __init__(self, ctx, fixed, free_planet, free_elem, hill_factor, dims=0):
+        self.ctx = ctx
+        fixed = _f64(fixed).reshape(-1, len(ELEMS))
+        self.n_planets = fixed.shape[0]
+        fp = np.ascontiguousarray(free_planet, dtype=np.int32)
+        fe = np.ascontiguousarray(free_elem, dtype=np.int32)
+        self.nvars = len(fp)
+        h = C.c_void_p()
+        ctx.check(ctx.lib.rv_model_create(ctx.h, self.n_planets, _ptr(fixed), self.nvars, _ptr(fp), _ptr(fe),
+                                          float(hill_factor), int(dims), C.byref(h)), "rv_model_create")
+        self.h = h
+
+    def set_option(self, key, value):
+        self.ctx.check(self.ctx.lib.rv_model_set_option(self.h, key.encode(), float(value)), "rv_model_set_option")
+
+    def loglik(self, obs, theta):
+        """theta[W][nvars] (host) -> (logp[W], status[W]); State.get_logp for a batch."""
+        theta = _f64(theta).reshape(-1, max(self.nvars, 1)) if self.nvars else _f64(theta).reshape(-1, 0)
+        W = theta.shape[0]
+        logp = np.empty(W, dtype=np.float64)
+        status = np.empty(W, dtype=np.int32)
+        self.ctx.check(self.ctx.lib.rv_loglik(self.ctx.h, self.h, obs.h, _ptr(theta), W, _ptr(logp), _ptr(status)),
+                       "rv_loglik")
+        return logp, status
+
+    def loglik_dev(self, obs, d_theta, W, d_logp, d_status, stream=None):
+        """Device-pointer variant (ints from torch .data_ptr()), asynchronous on `stream`."""
+        self.ctx.check(self.ctx.lib.rv_loglik_dev(self.ctx.h, self.h, obs.h, C.c_void_p(d_theta), int(W),
+                                                  C.c_void_p(d_logp), C.c_void_p(d_status),
+                                                  C.c_void_p(stream) if stream else None), "rv_loglik_dev")
+
+    def rv_curve(self, theta, times):
+        """theta[W][nvars], times[nt] -> (rv[W][nt], status[W]); State.get_rv for a batch."""
+        theta = _f64(theta).reshape(-1, max(self.nvars, 1)) if self.nvars else _f64(theta).reshape(-1, 0)
+        times = _f64(times)
+        W, nt = theta.shape[0], len(times)
+        rv = np.zeros((W, nt), dtype=np.float64)
+        status = np.empty(W, dtype=np.int32)
+        self.ctx.check(self.ctx.lib.rv_rv_curve(self.ctx.h, self.h, _ptr(theta), W, _ptr(times), nt, _ptr(rv),
+                                                _ptr(status)), "rv_rv_curve")
+        return rv, status
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.ctx.lib.rv_model_destroy(self.h)
+            self.h = None
+
+
+_default_ctx = None
+
+
+def default_context():
+    """Process-wide context on cuda:LOCAL_RANK (or 0)."""
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context(int(os.environ.get("LOCAL_RANK", "0")))
+    return _default_ctx
+
+
+def set_default_context(ctx):
+    global _default_ctx
+    _default_ctx = ctx

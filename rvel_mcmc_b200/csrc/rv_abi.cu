@@ -1,0 +1,331 @@
+// rv_abi.cu -- the extern "C" boundary of librvgpu.so (see include/rvgpu.h).
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <new>
+#include "../../include/rvgpu.h"
+#include "rv_launch.h"
+#include "rv_loglik.cuh"
+#include "rv_model.h"
+
+struct rv_ctx {
+    int device;
+    int num_sms, cc_major, cc_minor, clock_khz;
+    cudaStream_t stream;
+    unsigned long long* d_item_counter;   // work-queue head
+    unsigned long long* d_work;           // [2] force evaluations, step attempts
+    int count_work;
+    // grow-only scratch
+    double* d_theta; size_t cap_theta;
+    double* d_logp; size_t cap_logp;
+    int* d_status; size_t cap_status;
+    double* d_part; size_t cap_part;
+    int* d_pstat; size_t cap_pstat;
+    double* d_times; size_t cap_times;
+    double* d_rv; size_t cap_rv;
+    char err[512];
+};
+struct rv_obs {
+    rv_ctx* ctx;
+    double *d_t, *d_rv, *d_err;   // forward [0,nf) then backward [nf,nf+nb)
+    int nf, nb;
+    double npoints;
+};
+struct rv_model {
+    rv_ctx* ctx;
+    rv::Model h;
+    rv::Model* d;
+    int mapping;
+};
+
+static char g_err[512] = "";
+
+static int fail(rv_ctx* ctx, int code, const char* fmt, ...) {
+    char* dst = ctx ? ctx->err : g_err;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(dst, 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CU(ctx, call)                                                                              \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) return fail(ctx, -100, "%s: %s", #call, cudaGetErrorString(e__)); \
+    } while (0)
+
+template <class T>
+static int ensure(rv_ctx* ctx, T** p, size_t* cap, size_t n) {
+    if (n <= *cap) return 0;
+    if (*p) cudaFree(*p);
+    *p = nullptr; *cap = 0;
+    size_t want = n + n / 4 + 64;
+    CU(ctx, cudaMalloc((void**)p, want * sizeof(T)));
+    *cap = want;
+    return 0;
+}
+
+extern "C" {
+
+const char* rv_last_error(const rv_ctx* ctx) { return ctx ? ctx->err : g_err; }
+
+int rv_ctx_create(int device, rv_ctx** out) {
+    if (!out) return fail(nullptr, -1, "rv_ctx_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(nullptr, -10, "rv_ctx_create: no CUDA device (%s); librvgpu has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (device < 0 || device >= n) return fail(nullptr, -11, "rv_ctx_create: device %d out of range (0..%d)", device, n - 1);
+    rv_ctx* c = new (std::nothrow) rv_ctx();
+    if (!c) return fail(nullptr, -12, "rv_ctx_create: out of host memory");
+    memset(c, 0, sizeof(*c));
+    c->device = device;
+    CU(nullptr, cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(nullptr, cudaGetDeviceProperties(&prop, device));
+    c->num_sms = prop.multiProcessorCount;
+    c->cc_major = prop.major; c->cc_minor = prop.minor;
+    int khz = 0;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
+    c->clock_khz = khz;
+    if (prop.major != 10) {
+        delete c;
+        return fail(nullptr, -13, "rv_ctx_create: device %d is sm_%d%d; this library carries sm_100a code only", device, prop.major, prop.minor);
+    }
+    CU(nullptr, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU(nullptr, cudaMalloc((void**)&c->d_item_counter, sizeof(unsigned long long)));
+    CU(nullptr, cudaMalloc((void**)&c->d_work, 2 * sizeof(unsigned long long)));
+    CU(nullptr, cudaMemset(c->d_item_counter, 0, sizeof(unsigned long long)));
+    CU(nullptr, cudaMemset(c->d_work, 0, 2 * sizeof(unsigned long long)));
+    *out = c;
+    return 0;
+}
+
+int rv_ctx_destroy(rv_ctx* c) {
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    cudaFree(c->d_item_counter); cudaFree(c->d_work);
+    cudaFree(c->d_theta); cudaFree(c->d_logp); cudaFree(c->d_status); cudaFree(c->d_part);
+    cudaFree(c->d_pstat); cudaFree(c->d_times); cudaFree(c->d_rv);
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return 0;
+}
+
+int rv_device_info(const rv_ctx* c, int* sm_count, int* cc_major, int* cc_minor, int* clock_khz) {
+    if (!c) return -1;
+    if (sm_count) *sm_count = c->num_sms;
+    if (cc_major) *cc_major = c->cc_major;
+    if (cc_minor) *cc_minor = c->cc_minor;
+    if (clock_khz) *clock_khz = c->clock_khz;
+    return 0;
+}
+
+int rv_obs_create(rv_ctx* ctx, const double* tf, const double* rvf, const double* errf, int nf,
+                  const double* tb, const double* rvb, const double* errb, int nb, double npoints,
+                  rv_obs** out) {
+    if (!ctx || !out) return fail(ctx, -1, "rv_obs_create: NULL argument");
+    if (nf < 0 || nb < 0 || nf + nb == 0) return fail(ctx, -2, "rv_obs_create: empty observation set");
+    if (nf + nb > 8000) return fail(ctx, -3, "rv_obs_create: %d epochs exceed the shared-memory staging limit (8000)", nf + nb);
+    CU(ctx, cudaSetDevice(ctx->device));
+    rv_obs* o = new (std::nothrow) rv_obs();
+    if (!o) return fail(ctx, -12, "out of host memory");
+    o->ctx = ctx; o->nf = nf; o->nb = nb; o->npoints = npoints;
+    const size_t n = (size_t)nf + nb;
+    CU(ctx, cudaMalloc((void**)&o->d_t, 3 * n * sizeof(double)));
+    o->d_rv = o->d_t + n; o->d_err = o->d_t + 2 * n;
+    const double* srcs[3][2] = {{tf, tb}, {rvf, rvb}, {errf, errb}};
+    double* dsts[3] = {o->d_t, o->d_rv, o->d_err};
+    for (int a = 0; a < 3; a++) {
+        if (nf) CU(ctx, cudaMemcpyAsync(dsts[a], srcs[a][0], nf * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        if (nb) CU(ctx, cudaMemcpyAsync(dsts[a] + nf, srcs[a][1], nb * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = o;
+    return 0;
+}
+
+int rv_obs_destroy(rv_obs* o) {
+    if (!o) return 0;
+    cudaSetDevice(o->ctx->device);
+    cudaFree(o->d_t);
+    delete o;
+    return 0;
+}
+
+int rv_model_create(rv_ctx* ctx, int n_planets, const double* fixed, int nvars, const int32_t* free_planet,
+                    const int32_t* free_elem, double hill_factor, int dims, rv_model** out) {
+    if (!ctx || !out || !fixed) return fail(ctx, -1, "rv_model_create: NULL argument");
+    rv_model* m = new (std::nothrow) rv_model();
+    if (!m) return fail(ctx, -12, "out of host memory");
+    m->ctx = ctx; m->mapping = 0; m->d = nullptr;
+    const int rc = rv::build_model(&m->h, n_planets, fixed, nvars, free_planet, free_elem, hill_factor, dims);
+    if (rc) {
+        delete m;
+        return fail(ctx, rc, "rv_model_create: invalid model (code %d): planets must be 1..%d, slots unique and in range, dims 0/2/3", rc, rv::MAXP);
+    }
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaMalloc((void**)&m->d, sizeof(rv::Model)));
+    CU(ctx, cudaMemcpy(m->d, &m->h, sizeof(rv::Model), cudaMemcpyHostToDevice));
+    *out = m;
+    return 0;
+}
+
+int rv_model_destroy(rv_model* m) {
+    if (!m) return 0;
+    cudaSetDevice(m->ctx->device);
+    cudaFree(m->d);
+    delete m;
+    return 0;
+}
+
+int rv_model_set_option(rv_model* m, const char* key, double value) {
+    if (!m || !key) return -1;
+    rv_ctx* ctx = m->ctx;
+    if (!strcmp(key, "dt0")) m->h.dt0 = value;
+    else if (!strcmp(key, "epsilon")) m->h.epsilon = value;
+    else if (!strcmp(key, "max_attempts")) m->h.max_attempts = (int)value;
+    else if (!strcmp(key, "hill_factor")) m->h.hill_factor = value;
+    else if (!strcmp(key, "mapping")) m->mapping = (int)value;
+    else return fail(ctx, -20, "rv_model_set_option: unknown key '%s'", key);
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaMemcpy(m->d, &m->h, sizeof(rv::Model), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+static int loglik_dev_impl(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, const double* d_theta,
+                           int64_t W, double* d_logp, int32_t* d_status, cudaStream_t s) {
+    if (W == 0) return 0;
+    if (int rc = ensure(ctx, &ctx->d_part, &ctx->cap_part, (size_t)(2 * W))) return rc;
+    if (int rc = ensure(ctx, &ctx->d_pstat, &ctx->cap_pstat, (size_t)(2 * W))) return rc;
+    rv::LoglikArgs a;
+    memset(&a, 0, sizeof a);
+    a.model = model->d; a.theta = d_theta; a.W = W;
+    a.ot = obs->d_t; a.orv = obs->d_rv; a.oerr = obs->d_err; a.nf = obs->nf; a.nb = obs->nb;
+    a.times = nullptr; a.nt = 0; a.rv_out = nullptr;
+    a.part_chi2 = ctx->d_part; a.part_status = ctx->d_pstat;
+    a.item_counter = ctx->d_item_counter;
+    a.work_counters = ctx->count_work ? ctx->d_work : nullptr;
+    CU(ctx, rv::launch_loglik(a, model->h.P, model->h.D, model->mapping, ctx->num_sms, s));
+    CU(ctx, rv::launch_finalize(ctx->d_part, ctx->d_pstat, W, obs->npoints, d_logp, d_status, ctx->d_item_counter, s));
+    return 0;
+}
+
+int rv_loglik_dev(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, const double* d_theta, int64_t W,
+                  double* d_logp, int32_t* d_status, void* stream) {
+    if (!ctx || !model || !obs) return fail(ctx, -1, "rv_loglik_dev: NULL handle");
+    if (W < 0) return fail(ctx, -2, "rv_loglik_dev: negative W");
+    CU(ctx, cudaSetDevice(ctx->device));
+    return loglik_dev_impl(ctx, model, obs, d_theta, W, d_logp, d_status, stream ? (cudaStream_t)stream : ctx->stream);
+}
+
+int rv_loglik(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, const double* theta, int64_t W,
+              double* logp, int32_t* status) {
+    if (!ctx || !model || !obs) return fail(ctx, -1, "rv_loglik: NULL handle");
+    if (W < 0) return fail(ctx, -2, "rv_loglik: negative W");
+    if (W == 0) return 0;
+    if (!theta || !logp || !status) return fail(ctx, -1, "rv_loglik: NULL buffer");
+    CU(ctx, cudaSetDevice(ctx->device));
+    const size_t nv = (size_t)(model->h.nvars > 0 ? model->h.nvars : 1);
+    if (int rc = ensure(ctx, &ctx->d_theta, &ctx->cap_theta, (size_t)W * nv)) return rc;
+    if (int rc = ensure(ctx, &ctx->d_logp, &ctx->cap_logp, (size_t)W)) return rc;
+    if (int rc = ensure(ctx, &ctx->d_status, &ctx->cap_status, (size_t)W)) return rc;
+    cudaStream_t s = ctx->stream;
+    if (model->h.nvars > 0)
+        CU(ctx, cudaMemcpyAsync(ctx->d_theta, theta, (size_t)W * model->h.nvars * sizeof(double), cudaMemcpyHostToDevice, s));
+    if (int rc = loglik_dev_impl(ctx, model, obs, ctx->d_theta, W, ctx->d_logp, ctx->d_status, s)) return rc;
+    CU(ctx, cudaMemcpyAsync(logp, ctx->d_logp, (size_t)W * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CU(ctx, cudaMemcpyAsync(status, ctx->d_status, (size_t)W * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    CU(ctx, cudaStreamSynchronize(s));
+    return 0;
+}
+
+int rv_rv_curve(rv_ctx* ctx, const rv_model* model, const double* theta, int64_t W, const double* times,
+                int nt, double* rv, int32_t* status) {
+    if (!ctx || !model) return fail(ctx, -1, "rv_rv_curve: NULL handle");
+    if (W < 0 || nt < 0) return fail(ctx, -2, "rv_rv_curve: negative size");
+    if (W == 0) return 0;
+    CU(ctx, cudaSetDevice(ctx->device));
+    const size_t nv = (size_t)(model->h.nvars > 0 ? model->h.nvars : 1);
+    if (int rc = ensure(ctx, &ctx->d_theta, &ctx->cap_theta, (size_t)W * nv)) return rc;
+    if (int rc = ensure(ctx, &ctx->d_pstat, &ctx->cap_pstat, (size_t)W)) return rc;
+    if (int rc = ensure(ctx, &ctx->d_times, &ctx->cap_times, (size_t)(nt > 0 ? nt : 1))) return rc;
+    if (int rc = ensure(ctx, &ctx->d_rv, &ctx->cap_rv, (size_t)W * (size_t)(nt > 0 ? nt : 1))) return rc;
+    cudaStream_t s = ctx->stream;
+    if (model->h.nvars > 0)
+        CU(ctx, cudaMemcpyAsync(ctx->d_theta, theta, (size_t)W * model->h.nvars * sizeof(double), cudaMemcpyHostToDevice, s));
+    if (nt) CU(ctx, cudaMemcpyAsync(ctx->d_times, times, (size_t)nt * sizeof(double), cudaMemcpyHostToDevice, s));
+    CU(ctx, cudaMemsetAsync(ctx->d_rv, 0, (size_t)W * (size_t)(nt > 0 ? nt : 1) * sizeof(double), s));
+    rv::LoglikArgs a;
+    memset(&a, 0, sizeof a);
+    a.model = model->d; a.theta = ctx->d_theta; a.W = W;
+    a.nf = 0; a.nb = 0;
+    a.times = ctx->d_times; a.nt = nt; a.rv_out = ctx->d_rv;
+    a.part_chi2 = nullptr; a.part_status = ctx->d_pstat;
+    a.item_counter = ctx->d_item_counter;
+    a.work_counters = ctx->count_work ? ctx->d_work : nullptr;
+    CU(ctx, rv::launch_loglik(a, model->h.P, model->h.D, model->mapping, ctx->num_sms, s));
+    CU(ctx, rv::launch_curve_finalize(ctx->d_item_counter, s));
+    if (nt) CU(ctx, cudaMemcpyAsync(rv, ctx->d_rv, (size_t)W * nt * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CU(ctx, cudaMemcpyAsync(status, ctx->d_pstat, (size_t)W * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    CU(ctx, cudaStreamSynchronize(s));
+    return 0;
+}
+
+int rv_count_work(rv_ctx* ctx, int enable) {
+    if (!ctx) return -1;
+    ctx->count_work = enable ? 1 : 0;
+    return 0;
+}
+
+int rv_work_counters(rv_ctx* ctx, uint64_t out[2], int reset) {
+    if (!ctx) return -1;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, cudaDeviceSynchronize());
+    unsigned long long h[2];
+    CU(ctx, cudaMemcpy(h, ctx->d_work, sizeof h, cudaMemcpyDeviceToHost));
+    if (out) { out[0] = h[0]; out[1] = h[1]; }
+    if (reset) CU(ctx, cudaMemset(ctx->d_work, 0, sizeof h));
+    return 0;
+}
+
+int rv_fp64_peak(rv_ctx* ctx, double* tflops) {
+    if (!ctx || !tflops) return -1;
+    CU(ctx, cudaSetDevice(ctx->device));
+    double* d = nullptr;
+    CU(ctx, cudaMalloc((void**)&d, 64));
+    cudaEvent_t e0, e1;
+    CU(ctx, cudaEventCreate(&e0));
+    CU(ctx, cudaEventCreate(&e1));
+    const int blocks = ctx->num_sms * 8, iters = 4096;
+    double best = 0.0;
+    for (int rep = 0; rep < 6; rep++) {
+        CU(ctx, cudaEventRecord(e0, ctx->stream));
+        CU(ctx, rv::launch_fp64_peak(d, blocks, iters, ctx->stream));
+        CU(ctx, cudaEventRecord(e1, ctx->stream));
+        CU(ctx, cudaEventSynchronize(e1));
+        float ms = 0;
+        CU(ctx, cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = 2.0 * 64.0 * (double)iters * 256.0 * (double)blocks;
+        const double tf = flops / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d);
+    *tflops = best;
+    return 0;
+}
+
+int rv_sync(rv_ctx* ctx) {
+    if (!ctx) return -1;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+}  // extern "C"

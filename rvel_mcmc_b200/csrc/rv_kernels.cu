@@ -1,0 +1,141 @@
+// rv_kernels.cu -- sm_100a kernels for the batched RV log-likelihood (plain path: MH / affine sampler).
+//
+// loglik_kernel: persistent grid (resident CTAs x SM count); every lane group pulls (walker, leg)
+// items from a global counter and runs the IAS15 state machine of rv_loglik.cuh.  Observation epochs,
+// velocities and errors are staged once per CTA into shared memory; the rejected-step history (br/er)
+// lives in shared memory, strided per lane; everything else of the walker state is in registers.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include "rv_launch.h"
+#include "rv_loglik.cuh"
+
+namespace rv {
+
+struct DevFetch {
+    unsigned long long* ctr;
+    template <class G>
+    __device__ __forceinline__ long long operator()(const G& g) const {
+        unsigned long long v = 0;
+        if (g.rank == 0) v = atomicAdd(ctr, 1ull);
+        if (G::lanes > 1) v = __shfl_sync(g.mask, v, g.base);
+        return (long long)v;
+    }
+};
+struct DevAll {
+    __device__ __forceinline__ bool operator()(bool f) const { return __all_sync(0xffffffffu, f) != 0; }
+};
+
+template <int P, int D, int PL, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) loglik_kernel(const LoglikArgs a) {
+    extern __shared__ double sm[];
+    const int nobs = a.nf + a.nb;
+    double* st = sm;
+    double* srv = sm + nobs;
+    double* serr = sm + 2 * nobs;
+    double* hist = sm + 3 * nobs;
+    for (int i = threadIdx.x; i < nobs; i += NT) {
+        st[i] = a.ot[i];
+        srv[i] = a.orv[i];
+        serr[i] = a.oerr[i];
+    }
+    __syncthreads();
+    using W = Walker<P, D, PL>;
+    W w;
+    const int lane = threadIdx.x & 31;
+    w.grp.init(lane);
+    w.hist.p = hist + threadIdx.x;
+    w.hist.stride = NT;
+    const bool lane_active = (w.grp.base + W::G) <= 32;
+    DevFetch fetch{a.item_counter};
+    DevAll all;
+    run_items(w, a, st, srv, serr, fetch, all, lane_active);
+}
+
+__global__ void finalize_kernel(const double* __restrict__ part_chi2, const int* __restrict__ part_status,
+                                long long W, double npoints, double* __restrict__ logp,
+                                int* __restrict__ status, unsigned long long* item_counter) {
+    const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w == 0) *item_counter = 0ull;
+    if (w >= W) return;
+    const int sb = part_status[w], sf = part_status[W + w];
+    const int s = (sf != ST_OK) ? sf : sb;   // the reference integrates the forward leg first
+    status[w] = s;
+    // state.py:98: (chi2b + chi2f) / Npoints ; state.py:109: logp = -chi2
+    logp[w] = (s == ST_OK) ? -((part_chi2[w] + part_chi2[W + w]) / npoints) : -INFINITY;
+}
+
+__global__ void curve_finalize_kernel(unsigned long long* item_counter) { *item_counter = 0ull; }
+
+template <int P, int D, int PL, int NT, int MINB>
+static cudaError_t launch_one(const LoglikArgs& a, int num_sms, cudaStream_t stream) {
+    auto kern = loglik_kernel<P, D, PL, NT, MINB>;
+    const int nobs = a.nf + a.nb;
+    constexpr int NC = PL * D;
+    const size_t smem = sizeof(double) * ((size_t)3 * nobs + (size_t)14 * NC * NT);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem);
+    if (e != cudaSuccess) return e;
+    if (occ < 1) return cudaErrorLaunchOutOfResources;
+    constexpr int G = P / PL;
+    const long long groups_per_block = (long long)(NT / 32) * (32 / G);
+    const long long n_items = a.times ? a.W : 2 * a.W;
+    long long blocks = (long long)num_sms * occ;
+    const long long need = (n_items + groups_per_block - 1) / groups_per_block;
+    if (need < blocks) blocks = need;
+    if (blocks < 1) blocks = 1;
+    kern<<<(unsigned)blocks, NT, smem, stream>>>(a);
+    return cudaGetLastError();
+}
+
+// mapping: 0 = one lane per planet (default), 1 = one thread per walker
+cudaError_t launch_loglik(const LoglikArgs& a, int P, int D, int mapping, int num_sms, cudaStream_t stream) {
+    const int key = P * 100 + D * 10 + mapping;
+    switch (key) {
+        case 120: case 121: return launch_one<1, 2, 1, 128, 3>(a, num_sms, stream);
+        case 130: case 131: return launch_one<1, 3, 1, 128, 2>(a, num_sms, stream);
+        case 220: return launch_one<2, 2, 1, 128, 3>(a, num_sms, stream);
+        case 221: return launch_one<2, 2, 2, 128, 2>(a, num_sms, stream);
+        case 230: return launch_one<2, 3, 1, 128, 2>(a, num_sms, stream);
+        case 231: return launch_one<2, 3, 1, 128, 2>(a, num_sms, stream);
+        case 320: case 321: return launch_one<3, 2, 1, 128, 3>(a, num_sms, stream);
+        case 330: case 331: return launch_one<3, 3, 1, 128, 2>(a, num_sms, stream);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t launch_finalize(const double* part_chi2, const int* part_status, long long W, double npoints,
+                            double* logp, int* status, unsigned long long* item_counter, cudaStream_t stream) {
+    const int nt = 256;
+    const unsigned nb = (unsigned)((W + nt - 1) / nt);
+    finalize_kernel<<<nb ? nb : 1, nt, 0, stream>>>(part_chi2, part_status, W, npoints, logp, status, item_counter);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_curve_finalize(unsigned long long* item_counter, cudaStream_t stream) {
+    curve_finalize_kernel<<<1, 1, 0, stream>>>(item_counter);
+    return cudaGetLastError();
+}
+
+// ---- FP64 FMA-pipe peak microbenchmark (roofline denominator; MEASURED_PEAKS.json has no FP64 entry) ----
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, double seed) {
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+            a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+        }
+    }
+    const double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (s == 12345.678) out[0] = s;  // keep the chain alive
+}
+
+cudaError_t launch_fp64_peak(double* d_out, int blocks, int iters, cudaStream_t stream) {
+    fp64_peak_kernel<<<blocks, 256, 0, stream>>>(d_out, iters, 1.0);
+    return cudaGetLastError();
+}
+
+}  // namespace rv

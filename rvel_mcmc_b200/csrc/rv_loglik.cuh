@@ -1,0 +1,126 @@
+// rv_loglik.cuh -- work-item state machine around rv::Walker.
+//
+// A work item is one leg of one walker's likelihood evaluation: the reference builds a fresh
+// simulation per leg (state.py:90-91: get_rv(obs.tf) then get_rv(obs.tb)), so the two legs are
+// independent integrations.  Lane groups pull items from a global counter; each iteration of the warp
+// loop runs exactly one IAS15 step attempt for every group that is mid-integration, and the cheap
+// bookkeeping (epoch reached -> record RV / chi2, next epoch, next item) happens in between.
+#pragma once
+#include "rv_core.cuh"
+
+namespace rv {
+
+struct LoglikArgs {
+    const Model* model;
+    const double* theta;      // [W][nvars] row-major
+    long long W;
+    // observation epochs: forward leg [0,nf), backward leg [nf,nf+nb) (order of obs.tf / obs.tb)
+    const double* ot;
+    const double* orv;
+    const double* oerr;
+    int nf, nb;
+    // RV-curve mode (state.py:61-73 get_rv on arbitrary times): one item per walker, no prior test
+    const double* times;
+    int nt;
+    double* rv_out;           // [W][nt]
+    // per-item results
+    double* part_chi2;        // [2W]: item w = backward leg of walker w, item W+w = forward leg
+    int* part_status;         // [2W] (curve mode: [W])
+    unsigned long long* item_counter;
+    unsigned long long* work_counters;  // [0] force evaluations, [1] step attempts (may be null)
+};
+
+enum : int { PH_NEED_ITEM = 0, PH_ENTRY, PH_CHECK, PH_STEP, PH_DONE };
+
+// Fetch / WarpAll are policy objects: device = atomicAdd + shuffle / __all_sync, host mirror = trivial.
+template <int P, int D, int PL, class Fetch, class WarpAll>
+RV_D void run_items(Walker<P, D, PL>& w, const LoglikArgs& a, const double* st, const double* srv,
+                    const double* serr, Fetch& fetch, WarpAll& warp_all, bool lane_active) {
+    const bool curve = (a.times != nullptr);
+    const long long n_items = curve ? a.W : 2 * a.W;
+    const int max_attempts = a.model->max_attempts;
+    const int nvars = a.model->nvars;
+    const bool leader = (w.grp.rank == 0);
+    int phase = lane_active ? PH_NEED_ITEM : PH_DONE;
+    long long item = -1, wi = 0;
+    const double *lt = nullptr, *lrv = nullptr, *lerr = nullptr;
+    LegCursor c;
+    c.status = RUN; c.ie = 0; c.n = 0; c.attempts = 0; c.tmax = 0.0; c.last_full_dt = 0.0; c.chi2 = 0.0;
+
+    auto finish = [&](int status) {
+        if (leader) {
+            a.part_status[item] = status;
+            if (!curve) a.part_chi2[item] = c.chi2;
+#if defined(__CUDA_ARCH__)
+            if (a.work_counters) {
+                atomicAdd(&a.work_counters[0], w.n_force);
+                atomicAdd(&a.work_counters[1], w.n_attempt);
+            }
+#else
+            if (a.work_counters) { a.work_counters[0] += w.n_force; a.work_counters[1] += w.n_attempt; }
+#endif
+        }
+        phase = PH_NEED_ITEM;
+    };
+
+    for (;;) {
+        while (phase != PH_STEP && phase != PH_DONE) {
+            if (phase == PH_NEED_ITEM) {
+                item = fetch(w.grp);
+                if (item >= n_items) { phase = PH_DONE; break; }
+                if (curve) {
+                    wi = item; lt = a.times; lrv = nullptr; lerr = nullptr; c.n = a.nt;
+                } else if (item < a.W) {       // backward legs first: they are the longer ones
+                    wi = item; lt = st + a.nf; lrv = srv + a.nf; lerr = serr + a.nf; c.n = a.nb;
+                } else {
+                    wi = item - a.W; lt = st; lrv = srv; lerr = serr; c.n = a.nf;
+                }
+                w.n_force = 0; w.n_attempt = 0;
+                c.ie = 0; c.chi2 = 0.0; c.attempts = 0;
+                const int s = w.setup(a.model, a.theta + wi * nvars, !curve);
+                if (s != ST_OK) { finish(s); continue; }
+                phase = PH_ENTRY;
+            }
+            if (phase == PH_ENTRY) {            // sim.integrate(t) entry (rebound: reb_integrate)
+                if (c.ie == c.n) { finish(ST_OK); continue; }
+                c.tmax = lt[c.ie];
+                c.last_full_dt = w.dt;
+                w.dt_last_done = 0.0;
+                c.status = RUN;
+                if (w.template encounter<false>()) c.status = ST_ENCOUNTER;
+                phase = PH_CHECK;
+            }
+            if (phase == PH_CHECK) {
+                const int s = check_exit(w, c);
+                if (s < 0) { phase = PH_STEP; break; }
+                w.dt = c.last_full_dt;
+                if (s != ST_OK) { finish(s); continue; }
+                const double vx = w.star_vx();
+                if (!isfinite(vx)) { finish(ST_NONFINITE); continue; }
+                if (curve) {
+                    if (leader) a.rv_out[wi * a.nt + c.ie] = vx;
+                } else {
+                    const double r = vx - lrv[c.ie], er = lerr[c.ie];
+                    c.chi2 += (r * r) / (er * er);
+                }
+                c.ie++;
+                phase = PH_ENTRY;
+            }
+        }
+        if (warp_all(phase == PH_DONE)) break;
+        // one step attempt, executed by the whole warp in lock-step (see Walker::attempt)
+        const bool stepping = (phase == PH_STEP);
+        const int r = w.attempt(stepping);
+        if (stepping) {
+            c.attempts++;
+            if (c.attempts > max_attempts || !isfinite(w.dt) || w.dt == 0.0) {
+                finish(ST_NONFINITE);
+            } else if (r & 1) {
+                if (r & 2) c.status = ST_ENCOUNTER;
+                phase = PH_CHECK;
+            }
+        }
+    }
+}
+
+}  // namespace rv

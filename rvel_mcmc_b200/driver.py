@@ -1,0 +1,179 @@
+"""driver -- Python-3 mirror of the reference's driver.py loops and diagnostics (no plotting).
+
+run_mh / run_emcee / run_smala / run_alsmala keep the reference's loop shape, chain layout and
+McmcBundle fields (driver.py:20-200); the autocorrelation-time, efficacy and KS helpers keep its
+definitions (driver.py:37-44, 343-425).  Plot functions are out of scope (matplotlib is not a
+dependency of the hot path).
+"""
+import hashlib
+from datetime import datetime
+
+import numpy as np
+
+from . import mcmc, observations
+
+
+class McmcBundle(object):
+    def __init__(self, mcmc, chain, chainlogp, clocktimes, obs, Niter, initial_state, trimmedchain=None,
+                 trimmedchainlogp=None, actimes=None, is_emcee=False, Nwalkers=32):
+        self.mcmc = mcmc
+        self.mcmc_is_emcee = is_emcee
+        self.mcmc_Nwalkers = Nwalkers
+        self.mcmc_chain = chain
+        self.mcmc_chainlogp = chainlogp
+        self.mcmc_clocktimes = clocktimes
+        self.mcmc_obs = obs
+        self.mcmc_Niter = Niter
+        self.mcmc_initial_state = initial_state
+        self.mcmc_trimmedchain = trimmedchain
+        self.mcmc_trimmedchainlogp = trimmedchainlogp
+        self.mcmc_actimes = actimes
+
+
+def auto_correlation(x):
+    x = np.asarray(x)
+    y = x - x.mean()
+    result = np.correlate(y, y, mode='full')
+    result = result[len(result) // 2:]
+    result /= result[0]
+    return result
+
+
+def _run_id(true_state, label):
+    h = hashlib.md5()
+    h.update(str(true_state.planets).encode())
+    h.update(str(label).encode())
+    return h
+
+
+def _single_chain(sampler, label, Niter, true_state, obs, printing_every, stepper=None):
+    chain = np.zeros((Niter + 1, sampler.state.Nvars))
+    chainlogp = np.zeros(Niter + 1)
+    tries = 0
+    clocktimes = [datetime.utcnow()]
+    chainlogp[0] = true_state.get_logp(obs)
+    chain[0] = true_state.get_params()
+    for i in range(Niter):
+        if (stepper(i) if stepper else sampler.step()):
+            tries += 1
+        chainlogp[i + 1] = sampler.state.get_logp(obs)
+        chain[i + 1] = sampler.state.get_params()
+        if i % printing_every == 1:
+            print("Progress: {p:.5}%, {n} accepted steps have been made, time: {t}".format(
+                p=100. * (float(i) / Niter), t=datetime.utcnow(), n=tries))
+            clocktimes.append(datetime.utcnow())
+    clocktimes.append(datetime.utcnow())
+    print("Acceptance rate: %.3f%%" % ((tries / float(Niter)) * 100))
+    h = _run_id(true_state, label)
+    return McmcBundle(sampler, chain, chainlogp, clocktimes, obs, Niter, true_state), h
+
+
+def run_mh(label, Niter, true_state, obs, scal, step, printing_every=400):
+    mh = mcmc.Mh(true_state, obs)
+    mh.set_scales(scal)
+    mh.step_size = step
+    return _single_chain(mh, label, Niter, true_state, obs, printing_every)
+
+
+def run_emcee(label, Niter, true_state, obs, Nwalkers, scal, printing_every=400):
+    ens = mcmc.Ensemble(true_state, obs, scales=scal, nwalkers=Nwalkers)
+    nsteps = int(Niter / Nwalkers)
+    listchain = np.zeros((Nwalkers, ens.state.Nvars, nsteps))
+    listchainlogp = np.zeros((Nwalkers, nsteps))
+    clocktimes = [datetime.utcnow()]
+    for i in range(nsteps):
+        ens.step()
+        listchainlogp[:, i] = ens.lnprob
+        listchain[:, :, i] = ens.states
+        if i % printing_every == 1:
+            print("Progress: {p:.5}%, time: {t}".format(p=100. * (float(i) / nsteps), t=datetime.utcnow()))
+            clocktimes.append(datetime.utcnow())
+    clocktimes.append(datetime.utcnow())
+    print("Error(s): {e}".format(e=ens.totalErrorCount))
+    h = _run_id(true_state, label)
+    # walker-major concatenation, as driver.py:108-112
+    chain = np.concatenate([listchain[i] for i in range(Nwalkers)], axis=1)
+    chainlogp = np.concatenate([listchainlogp[i] for i in range(Nwalkers)])
+    bundle = McmcBundle(ens, np.transpose(chain), chainlogp, clocktimes, obs, Niter, true_state, is_emcee=True,
+                        Nwalkers=Nwalkers)
+    return bundle, h
+
+
+def run_smala(label, Niter, true_state, obs, eps, alpha, printing_every=40):
+    smala = mcmc.Smala(true_state, obs, eps, alpha)
+    return _single_chain(smala, label, Niter, true_state, obs, printing_every)
+
+
+def run_alsmala(label, Niter, true_state, obs, eps, alpha, bern_a, bern_b, printing_every=40):
+    alsmala = mcmc.Alsmala(true_state, obs, eps, alpha)
+
+    def stepper(i):
+        if np.exp(-bern_a * i / Niter) > np.random.uniform():
+            return alsmala.step()
+        return alsmala.step_mala()
+    return _single_chain(alsmala, label, Niter, true_state, obs, printing_every, stepper)
+
+
+def create_obs(state, npoint, err, errVar, t):
+    return observations.FakeObservation(state, Npoints=npoint, error=err, errorVar=errVar, tmax=t)
+
+
+def read_obs(filen):
+    return observations.Observation_FromFile(filename=filen, Npoints=100)
+
+
+def save_obs(obs, true_state, label):
+    """.vels writer (driver.py:215-222; the reference writes the rv column twice -- fixed here: col3 = err)."""
+    col1 = obs.t / 1.720e-2
+    col2 = obs.rv / 3.355e-5
+    col3 = obs.err / 3.355e-5
+    h = _run_id(true_state, label)
+    name = 'obs_{ha}.vels'.format(ha=h.hexdigest())
+    np.savetxt(name, np.c_[col1, col2, col3])
+    return name
+
+
+def ac_time(series):
+    """First lag at which the normalised autocorrelation drops below 0.5 (driver.py:366-377)."""
+    r = auto_correlation(series)
+    below = np.nonzero(r < 0.5)[0]
+    return int(below[0]) if len(below) else len(r)
+
+
+def ac_times(bundle):
+    """Per-parameter AC times; for ensemble chains the mean over walkers (driver.py:355-370)."""
+    chain = bundle.mcmc_chain
+    nv = chain.shape[1]
+    out = np.zeros(nv)
+    if bundle.mcmc_is_emcee:
+        nw = bundle.mcmc_Nwalkers
+        per = chain.shape[0] // nw
+        for j in range(nv):
+            out[j] = np.mean([ac_time(chain[w * per:(w + 1) * per, j]) for w in range(nw)])
+    else:
+        for j in range(nv):
+            out[j] = ac_time(chain[:, j])
+    bundle.mcmc_actimes = out
+    return out
+
+
+def efficacy(bundle):
+    """Niter / (wall seconds * max AC time) (driver.py:412-414)."""
+    dt = (bundle.mcmc_clocktimes[-1] - bundle.mcmc_clocktimes[0]).total_seconds()
+    act = bundle.mcmc_actimes if bundle.mcmc_actimes is not None else ac_times(bundle)
+    return bundle.mcmc_Niter / (dt * np.max(act))
+
+
+def calc_kstatistic(chain_a, chain_b):
+    """Two-sample KS statistic per parameter (driver.py:423-425)."""
+    from scipy import stats
+    return [stats.ks_2samp(chain_a[:, i], chain_b[:, i])[0] for i in range(chain_a.shape[1])]
+
+
+def save_data(bundle, h):
+    np.save('chain_{ha}.npy'.format(ha=h.hexdigest()), bundle.mcmc_chain)
+    np.save('chainlogp_{ha}.npy'.format(ha=h.hexdigest()), bundle.mcmc_chainlogp)
+
+
+def load_data(hexdigest):
+    return np.load('chain_{ha}.npy'.format(ha=hexdigest)), np.load('chainlogp_{ha}.npy'.format(ha=hexdigest))

@@ -1,0 +1,192 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (ctypes -> librvgpu.so), against the
+CPU oracle and the reference's golden values.  Tolerances are north_star's: RVs within 1e-9 relative,
+log-likelihood within 1e-6 absolute; statuses (prior / Encounter) must match exactly."""
+import numpy as np
+import pytest
+
+import rvtest as T
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from rvel_mcmc_b200 import _abi
+    c = _abi.Context(0)
+    yield c
+    c.close()
+
+
+def _obs_handle(ctx, obs):
+    from rvel_mcmc_b200 import _abi
+    return _abi.ObsHandle(ctx, obs.tf, obs.rvf, obs.errorf, obs.tb, obs.rvb, obs.errorb, obs.Npoints)
+
+
+def _model(ctx, fixed, fp, fe, hill, dims=0, mapping=0):
+    from rvel_mcmc_b200 import _abi
+    m = _abi.ModelHandle(ctx, fixed, fp, fe, hill, dims)
+    if mapping:
+        m.set_option("mapping", mapping)
+    return m
+
+
+@pytest.mark.parametrize("mapping", [0, 1])
+def test_kat2_kat5_kat6_through_abi(ctx, mapping):
+    obs = T.load_vels("HD155358.vels")
+    oh = _obs_handle(ctx, obs)
+    m = _model(ctx, np.zeros((2, 7)), T.FP10, T.FE10, 2.0, mapping=mapping)
+    theta = np.array([T.HD_SOL, T.KAT6_VEC] + [v for v, _ in T.KAT5])
+    logp, st = m.loglik(oh, theta)
+    assert list(st) == [0, 0, 3, 3, 3]
+    assert abs(logp[0] - T.KAT2_LOGP) < 5e-11          # (Ex)HD155358.ipynb:149
+    assert abs(logp[1] - T.KAT6_LOGP) < 5e-6
+    assert np.all(np.isneginf(logp[2:]))
+
+
+@pytest.mark.parametrize("fn,planets", [("rvcurve_ben_2-1.txt", T.KAT3_PLANETS), ("rvcurve_ben_3-1.txt", T.KAT4_PLANETS)])
+def test_kat3_kat4_rv_curves_through_abi(ctx, fn, planets):
+    obs = T.load_vels("TEST_2-1_COMPACT.vels")
+    tg, rg = T.load_rvcurve(fn)
+    times = np.linspace(obs.tb[0], obs.tf[-1], 1000)
+    m = _model(ctx, T.elems_from_planets(planets), [], [], 1.0)
+    rv, st = m.rv_curve(np.zeros((1, 0)), times)
+    assert st[0] == 0
+    assert np.abs(rv[0] - rg).max() / np.abs(rg).max() < 1e-9
+
+
+@pytest.mark.parametrize("mapping", [0, 1])
+def test_walker_ball_matches_oracle(ctx, mapping):
+    # HD155358 shape (config 2): Gaussian ball of walkers around the published solution, both hill factors
+    obs = T.load_vels("HD155358.vels")
+    oh = _obs_handle(ctx, obs)
+    theta = T.gaussian_ball(T.HD_SOL, T.HD_SCALE_VEC, 512, 11)
+    theta[5, 3] = 1e-6            # prior violation (m)
+    theta[6, 0] = 0.01            # prior violation (a)
+    theta[7, 1] = 0.9; theta[7, 2] = 0.6   # h^2+k^2 >= 1
+    for hill in (1.0, 2.0):
+        m = _model(ctx, np.zeros((2, 7)), T.FP10, T.FE10, hill, mapping=mapping)
+        lg, sg = m.loglik(oh, theta)
+        lo, so, _ = T.orc_logp_batch(np.zeros((2, 7)), T.FP10, T.FE10, hill, obs, theta)
+        assert np.array_equal(sg, so)
+        assert list(sg[5:8]) == [1, 1, 1]
+        ok = so == 0
+        assert ok.sum() > 100
+        assert np.abs(lg[ok] - lo[ok]).max() < 1e-6
+        assert np.all(np.isneginf(lg[~ok]))
+
+
+def test_wide_ball_with_encounters_matches_oracle(ctx):
+    # a wide ball provokes Encounter storms like the reference's emcee runs (HD155358.ipynb:123-149)
+    obs = T.load_vels("HD155358.vels")
+    oh = _obs_handle(ctx, obs)
+    theta = T.gaussian_ball(T.HD_SOL, T.HD_SCALE_VEC, 768, 5, width=0.5)
+    m = _model(ctx, np.zeros((2, 7)), T.FP10, T.FE10, 2.0)
+    lg, sg = m.loglik(oh, theta)
+    lo, so, _ = T.orc_logp_batch(np.zeros((2, 7)), T.FP10, T.FE10, 2.0, obs, theta)
+    assert (so == 3).sum() > 5 and (so == 0).sum() > 50
+    mism = np.nonzero(sg != so)[0]
+    # an encounter exactly at the threshold may flip on rounding; allow at most 1 in 768
+    assert len(mism) <= 1, (mism, sg[mism], so[mism])
+    ok = (so == 0) & (sg == 0)
+    assert np.abs(lg[ok] - lo[ok]).max() < 1e-6 * np.maximum(1.0, np.abs(lo[ok])).max()
+
+
+def test_results_do_not_depend_on_batch_composition(ctx):
+    # dynamic work distribution must not change a single bit of any walker's result
+    obs = T.load_vels("HD155358.vels")
+    oh = _obs_handle(ctx, obs)
+    theta = T.gaussian_ball(T.HD_SOL, T.HD_SCALE_VEC, 300, 3, width=0.2)
+    m = _model(ctx, np.zeros((2, 7)), T.FP10, T.FE10, 2.0)
+    l1, s1 = m.loglik(oh, theta)
+    perm = np.random.RandomState(0).permutation(300)
+    l2, s2 = m.loglik(oh, theta[perm])
+    assert np.array_equal(s1[perm], s2)
+    assert np.array_equal(l1[perm], l2)
+    l3, s3 = m.loglik(oh, theta[:7])
+    assert np.array_equal(l3, l1[:7]) and np.array_equal(s3, s1[:7])
+
+
+def test_one_three_planets_and_inclined(ctx):
+    rng = np.random.RandomState(3)
+    obs = T.Obs()
+    obs.tf = np.append([0], np.sort(rng.uniform(0, 6.0, 20))); obs.tb = np.sort(rng.uniform(0, -6.0, 20))
+    obs.rvf = 1e-4 * rng.normal(size=21); obs.rvb = 1e-4 * rng.normal(size=20)
+    obs.errorf = np.full(21, 3e-4); obs.errorb = np.full(20, 3e-4); obs.Npoints = 40
+    oh = _obs_handle(ctx, obs)
+    for planets in ([{"a": 0.35, "m": 0.001965}],
+                    [{"m": 0.92e-3, "a": 0.2275, "h": -0.06, "k": 0.015, "l": -1.0},
+                     {"m": 1.95e-3, "a": 0.3665, "h": 0.02, "k": 0.0, "l": 2.1},
+                     {"m": 1.1e-3, "a": 0.59, "h": 0.01, "k": 0.03, "l": 0.4}],
+                    [{"m": 0.92e-3, "a": 0.2275, "h": -0.06, "k": 0.015, "l": -1.0, "ix": 0.05, "iy": -0.02},
+                     {"m": 1.95e-3, "a": 0.3665, "h": 0.02, "k": 0.0, "l": 2.1, "ix": -0.03, "iy": 0.04}],
+                    [{"m": 0.92e-3, "a": 0.2275, "h": -0.06, "k": 0.015, "l": -1.0, "ix": 0.05, "iy": -0.02},
+                     {"m": 1.95e-3, "a": 0.3665, "h": 0.02, "k": 0.0, "l": 2.1, "ix": -0.03, "iy": 0.04},
+                     {"m": 1.1e-3, "a": 0.59, "h": 0.01, "k": 0.03, "l": 0.4, "ix": 0.01, "iy": 0.01}]):
+        E = T.elems_from_planets(planets)
+        so, lo = T.orc_logp(E, 1.0, obs)
+        m = _model(ctx, E, [], [], 1.0)
+        lg, sg = m.loglik(oh, np.zeros((3, 0)))
+        assert so == 0 and list(sg) == [0, 0, 0]
+        assert np.abs(lg - lo).max() < 1e-9 * max(1.0, abs(lo))
+        # D=3 engine on a coplanar system == D=2 engine
+        if len(planets[0]) <= 5:
+            m3 = _model(ctx, E, [], [], 1.0, dims=3)
+            l3, s3 = m3.loglik(oh, np.zeros((1, 0)))
+            assert abs(l3[0] - lg[0]) < 1e-10 * max(1.0, abs(lo))
+
+
+def test_edge_cases(ctx):
+    obs = T.load_vels("HD155358.vels")
+    oh = _obs_handle(ctx, obs)
+    m = _model(ctx, np.zeros((2, 7)), T.FP10, T.FE10, 2.0)
+    lg, sg = m.loglik(oh, np.zeros((0, 10)))          # empty batch
+    assert lg.shape == (0,) and sg.shape == (0,)
+    lg, sg = m.loglik(oh, np.array([T.HD_SOL]))       # single walker
+    assert sg[0] == 0
+    # ragged legs: forward leg only one epoch (t=0), long backward leg
+    o2 = T.Obs()
+    o2.tf = obs.tf[:1]; o2.rvf = obs.rvf[:1]; o2.errorf = obs.errorf[:1]
+    o2.tb = obs.tb; o2.rvb = obs.rvb; o2.errorb = obs.errorb; o2.Npoints = 100
+    l2, s2 = m.loglik(_obs_handle(ctx, o2), np.array([T.HD_SOL]))
+    so, lo = T.orc_logp(T.elems_from_planets(T.planets_from_vec(T.HD_SOL)), 2.0, o2)
+    assert s2[0] == so == 0 and abs(l2[0] - lo) < 1e-9
+    # duplicate epochs and an epoch equal to t=0 in the middle of a leg
+    o3 = T.Obs()
+    o3.tf = np.array([0.0, 0.5, 0.5, 1.25]); o3.rvf = np.zeros(4); o3.errorf = np.full(4, 1e-4)
+    o3.tb = np.array([-2.0, -1.0, 0.0]); o3.rvb = np.zeros(3); o3.errorb = np.full(3, 1e-4); o3.Npoints = 7
+    l3, s3 = m.loglik(_obs_handle(ctx, o3), np.array([T.HD_SOL]))
+    so, lo = T.orc_logp(T.elems_from_planets(T.planets_from_vec(T.HD_SOL)), 2.0, o3)
+    assert s3[0] == so == 0 and abs(l3[0] - lo) < 1e-6 * abs(lo)
+
+
+def test_state_api_on_gpu():
+    # the reference-facing classes: State.get_logp / get_rv / get_chi2 + Encounter exception
+    import os
+    from rvel_mcmc_b200 import observations, state, Encounter
+    obs = observations.Observation_FromFile(os.path.join(T.GOLDEN, "HD155358.vels"), Npoints=100)
+    s = state.State(T.planets_from_vec(T.HD_SOL))
+    s.hillRadiusFactor = 2.
+    assert abs(s.get_logp(obs) - T.KAT2_LOGP) < 5e-11
+    assert abs(-s.get_chi2(obs) - T.KAT2_LOGP) < 5e-11
+    rv = s.get_rv(obs.tf)
+    assert abs(rv[0] - (-0.00041883056816320016)) < 1e-15        # star vx at t=0 (KAT-1)
+    bad = state.State(T.planets_from_vec(T.KAT5[1][0]))
+    with pytest.raises(Encounter):
+        bad.get_logp(obs)
+    with pytest.raises(Encounter):
+        bad.get_rv(obs.tf)
+
+
+def test_million_walker_properties(ctx):
+    # full-size batch (BASELINE configs[4] lower range): size-independent properties
+    obs = T.load_vels("HD155358.vels")
+    oh = _obs_handle(ctx, obs)
+    m = _model(ctx, np.zeros((2, 7)), T.FP10, T.FE10, 2.0)
+    base = T.gaussian_ball(T.HD_SOL, T.HD_SCALE_VEC, 4096, 21)
+    theta = np.tile(base, (32, 1))                      # 131072 walkers, 32 copies of each vector
+    lg, sg = m.loglik(oh, theta)
+    lg = lg.reshape(32, 4096); sg = sg.reshape(32, 4096)
+    assert np.all(sg == sg[0]) and np.all(lg == lg[0])   # bit-identical replicas
+    lo, so, _ = T.orc_logp_batch(np.zeros((2, 7)), T.FP10, T.FE10, 2.0, obs, base[:64])
+    assert np.array_equal(so, sg[0, :64])
+    assert np.abs(lo - lg[0, :64])[so == 0].max() < 1e-6

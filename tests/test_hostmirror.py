@@ -1,0 +1,72 @@
+"""The kernel's per-walker engine (rv_core.cuh / rv_loglik.cuh) compiled for the host (test-only mirror,
+thread-per-walker mapping) against the independent CPU oracle.  Catches logic errors in the device source
+without a GPU; the GPU parity tests proper are in test_gpu_loglik.py."""
+import numpy as np
+
+import rvtest as T
+
+
+def _hd(nw, seed):
+    obs = T.load_vels("HD155358.vels")
+    theta = T.gaussian_ball(T.HD_SOL, T.HD_SCALE_VEC, nw, seed)
+    return obs, theta
+
+
+def test_mirror_kat2_and_counts():
+    obs = T.load_vels("HD155358.vels")
+    logp, st, cnt = T.mirror_loglik(np.zeros((2, 7)), T.FP10, T.FE10, 2.0, obs, np.array([T.HD_SOL]))
+    assert st[0] == 0
+    assert abs(logp[0] - T.KAT2_LOGP) < 5e-11
+    assert cnt[1] == 1913           # same step-attempt sequence as the oracle / SURVEY B.6
+    # coplanar specialisation == general 3-D path
+    logp3, st3, _ = T.mirror_loglik(np.zeros((2, 7)), T.FP10, T.FE10, 2.0, obs, np.array([T.HD_SOL]), dims=3)
+    assert abs(logp3[0] - logp[0]) < 1e-11
+
+
+def test_mirror_matches_oracle_on_walker_ball():
+    obs, theta = _hd(24, 7)
+    lo, so, _ = T.orc_logp_batch(np.zeros((2, 7)), T.FP10, T.FE10, 1.0, obs, theta)
+    lm, sm, _ = T.mirror_loglik(np.zeros((2, 7)), T.FP10, T.FE10, 1.0, obs, theta)
+    assert np.array_equal(so, sm)
+    ok = so == 0
+    assert ok.sum() > 0
+    assert np.abs(lo[ok] - lm[ok]).max() < 1e-6          # north_star: logp within 1e-6 absolute
+    assert np.all(np.isneginf(lm[~ok]))
+
+
+def test_mirror_encounters_and_prior():
+    obs = T.load_vels("HD155358.vels")
+    vecs = np.array([v for v, _ in T.KAT5] + [T.HD_SOL])
+    vecs[-1, 3] = 1e-6                 # m <= 5e-6 -> prior
+    lm, sm, _ = T.mirror_loglik(np.zeros((2, 7)), T.FP10, T.FE10, 2.0, obs, vecs)
+    assert list(sm) == [3, 3, 3, 1]
+    assert np.all(np.isneginf(lm))
+
+
+def test_mirror_rv_curve_kat3():
+    obs = T.load_vels("TEST_2-1_COMPACT.vels")
+    tg, rg = T.load_rvcurve("rvcurve_ben_2-1.txt")
+    E = T.elems_from_planets(T.KAT3_PLANETS)
+    times = np.linspace(obs.tb[0], obs.tf[-1], 1000)
+    rv, st = T.mirror_loglik(E, [], [], 1.0, obs, np.zeros((1, 0)), times=times)
+    assert st[0] == 0
+    assert np.abs(rv[0] - rg).max() / np.abs(rg).max() < 1e-9     # north_star: RVs within 1e-9 relative
+
+
+def test_mirror_one_and_three_planets():
+    rng = np.random.RandomState(3)
+    obs = T.Obs()
+    obs.tf = np.append([0], np.sort(rng.uniform(0, 6.0, 20))); obs.tb = np.sort(rng.uniform(0, -6.0, 20))
+    obs.rvf = 1e-4 * rng.normal(size=21); obs.rvb = 1e-4 * rng.normal(size=20)
+    obs.errorf = np.full(21, 3e-4); obs.errorb = np.full(20, 3e-4); obs.Npoints = 40
+    for planets in ([{"a": 0.35, "m": 0.001965}],
+                    [{"m": 0.92e-3, "a": 0.2275, "h": -0.06, "k": 0.015, "l": -1.0},
+                     {"m": 1.95e-3, "a": 0.3665, "h": 0.02, "k": 0.0, "l": 2.1},
+                     {"m": 1.1e-3, "a": 0.59, "h": 0.01, "k": 0.03, "l": 0.4}],
+                    [{"m": 0.92e-3, "a": 0.2275, "h": -0.06, "k": 0.015, "l": -1.0, "ix": 0.05, "iy": -0.02},
+                     {"m": 1.95e-3, "a": 0.3665, "h": 0.02, "k": 0.0, "l": 2.1, "ix": -0.03, "iy": 0.04}]):
+        E = T.elems_from_planets(planets)
+        so, lo = T.orc_logp(E, 1.0, obs)
+        lm, sm, _ = T.mirror_loglik(E, [], [], 1.0, obs, np.zeros((1, 0)))
+        assert so == sm[0] == 0
+        assert abs(lo - lm[0]) < 1e-9 * max(1.0, abs(lo))

@@ -1,0 +1,126 @@
+"""Pins the CPU oracle (oracle/rv_oracle.c) against every golden value the reference holds for the hot
+path.  Runs without a GPU."""
+import ctypes as C
+
+import numpy as np
+
+import rvtest as T
+
+
+def test_kat1_initial_conditions():
+    # (Ex)HD155358.ipynb:84-95 -- 16-digit Pal->cartesian and move_to_com values
+    E = T.elems_from_planets(T.planets_from_vec(T.HD_SOL))
+    com = np.zeros((3, 7))
+    rel = np.zeros((3, 7))
+    T.oracle().orc_initial_conditions(2, T.vp(E), T.vp(com), T.vp(rel))
+    # (vx, vy), (x, y) before the COM shift
+    np.testing.assert_allclose(rel[1, [4, 5]], [1.3456579647209153, -0.3111782879962493], rtol=0, atol=4e-16)
+    np.testing.assert_allclose(rel[1, [1, 2]], [-0.10040105549379322, -0.5750167691072843], rtol=0, atol=4e-16)
+    np.testing.assert_allclose(rel[2, [4, 5]], [-0.9273537426348033, 0.1621575850335594], rtol=0, atol=4e-16)
+    np.testing.assert_allclose(rel[2, [1, 2]], [0.29663305036469334, 1.0436376255071829], rtol=0, atol=4e-16)
+    # after move_to_com
+    np.testing.assert_allclose(com[0, [4, 5]], [-0.00041883056816320016, 0.00014019875566797076], rtol=2e-15, atol=0)   # a few ulp: rebound accumulates the COM pairwise
+    np.testing.assert_allclose(com[0, [1, 2]], [-0.00015729068590102283, -0.00035766924337062825], rtol=2e-15, atol=0)   # a few ulp: rebound accumulates the COM pairwise
+    np.testing.assert_allclose(com[1, [4, 5]], [1.345239134152752, -0.31103808924058135], rtol=0, atol=4e-16)
+    np.testing.assert_allclose(com[1, [1, 2]], [-0.10055834617969424, -0.5753744383506549], rtol=0, atol=4e-16)
+    np.testing.assert_allclose(com[2, [4, 5]], [-0.9277725732029665, 0.16229778378922738], rtol=0, atol=4e-16)
+    np.testing.assert_allclose(com[2, [1, 2]], [0.2964757596787923, 1.0432799562638122], rtol=0, atol=4e-16)
+    assert np.all(com[:, [3, 6]] == 0.0)
+
+
+def test_kat2_hd155358_logp():
+    # (Ex)HD155358.ipynb:149: -2.41616612321 (12 printed digits; Npoints=100, hillRadiusFactor=2).
+    # The 12th digit is at the integrator's own noise floor (an FMA-contracted build of the same C moves it by
+    # 1.4e-11), so the pin is 5e-11 absolute -- 4 orders tighter than north_star's 1e-6.
+    obs = T.load_vels("HD155358.vels")
+    E = T.elems_from_planets(T.planets_from_vec(T.HD_SOL))
+    st, logp, cnt, legs = T.orc_logp(E, 2.0, obs, counters=True)
+    assert st == 0 and legs == [0, 0]
+    assert abs(logp - T.KAT2_LOGP) < 5e-11
+    # SURVEY App. B.6 workload counts: 1913 step attempts (3 rejected)
+    assert cnt[1] == 1913 and cnt[2] == 3
+
+
+def test_kat6_weak_logp():
+    obs = T.load_vels("HD155358.vels")
+    E = T.elems_from_planets(T.planets_from_vec(T.KAT6_VEC))
+    st, logp = T.orc_logp(E, 1.0, obs)
+    assert st == 0
+    assert abs(logp - T.KAT6_LOGP) < 5e-6     # parameters were printed with 9 digits only
+
+
+def test_kat5_encounters():
+    obs = T.load_vels("HD155358.vels")
+    for vec, leg in T.KAT5:
+        E = T.elems_from_planets(T.planets_from_vec(vec))
+        for hill in (1.0, 2.0):
+            st, logp, cnt, legs = T.orc_logp(E, hill, obs, counters=True)
+            assert st == 3 and logp == -np.inf
+            assert legs == ([0, 3] if leg == "backward" else [3, 0])
+
+
+def test_kat3_kat4_rv_curves():
+    # plotArchive/Ben's 2-1/log_Ben-2-1:4 and Ben's 3-1/log_Ben-3-1:4 -- 1000-point REBOUND RV curves (12 digits)
+    obs = T.load_vels("TEST_2-1_COMPACT.vels")
+    for fn, planets in (("rvcurve_ben_2-1.txt", T.KAT3_PLANETS), ("rvcurve_ben_3-1.txt", T.KAT4_PLANETS)):
+        tg, rg = T.load_rvcurve(fn)
+        times = np.linspace(obs.tb[0], obs.tf[-1], 1000)        # state.py:79
+        assert np.abs(times - tg).max() < 1e-10
+        st, rv = T.orc_rv(T.elems_from_planets(planets), 1.0, times)
+        assert st == 0
+        assert np.abs(rv - rg).max() < 2e-14                      # print-precision limited
+        assert np.abs(rv - rg).max() / np.abs(rg).max() < 1e-11
+
+
+def test_prior_hard():
+    E = T.elems_from_planets(T.planets_from_vec(T.HD_SOL))
+    assert T.oracle().orc_prior_hard(2, T.vp(E)) == 0
+    for slot, val in ((1, 0.02), (0, 5e-6)):
+        B = E.copy(); B[1, slot] = val
+        assert T.oracle().orc_prior_hard(2, T.vp(B)) == 1
+    B = E.copy(); B[0, 2] = 0.8; B[0, 3] = 0.6
+    assert T.oracle().orc_prior_hard(2, T.vp(B)) == 1
+    B = E.copy(); B[0, 5] = 2.0
+    assert T.oracle().orc_prior_hard(2, T.vp(B)) == 1
+    obs = T.load_vels("HD155358.vels")
+    B = E.copy(); B[0, 0] = 1e-6
+    st, logp = T.orc_logp(B, 2.0, obs)
+    assert st == 1 and logp == -np.inf
+
+
+def test_variational_ics_match_finite_differences():
+    # vary(p,e) / vary(p,e1,e2) + move_to_com == exact derivatives of the barycentric ICs
+    E = T.elems_from_planets(T.planets_from_vec(T.HD_SOL))
+    fp = np.array(T.FP10, dtype=np.int32); fe = np.array(T.FE10, dtype=np.int32)
+    nv = 10
+    nsets = 1 + nv + nv * (nv + 1) // 2
+    out = np.zeros((nsets, 3, 7))
+    T.oracle().orc_var_initial_conditions(2, T.vp(E), nv, T.vp(fp), T.vp(fe), T.vp(out))
+
+    def ics(Em):
+        com = np.zeros((3, 7))
+        T.oracle().orc_initial_conditions(2, T.vp(Em), T.vp(com), None)
+        return com
+
+    def shifted(da):
+        Em = E.copy()
+        for v, d in da:
+            Em[fp[v], fe[v]] += d
+        return ics(Em)
+    for v in range(nv):
+        h = 1e-6 * max(abs(E[fp[v], fe[v]]), 1e-3)
+        fd = (shifted([(v, h)]) - shifted([(v, -h)])) / (2 * h)
+        np.testing.assert_allclose(out[1 + v], fd, rtol=2e-6, atol=1e-9)
+    idx = 0
+    for a in range(nv):
+        for b in range(a + 1):
+            ha = 1e-2 * max(abs(E[fp[a], fe[a]]), 1e-2)
+            hb = 1e-2 * max(abs(E[fp[b], fe[b]]), 1e-2)
+
+            def mixed(ha, hb):
+                return (shifted([(a, ha), (b, hb)]) - shifted([(a, ha), (b, -hb)]) - shifted([(a, -ha), (b, hb)])
+                        + shifted([(a, -ha), (b, -hb)])) / (4 * ha * hb)
+            fd = (4.0 * mixed(ha / 2, hb / 2) - mixed(ha, hb)) / 3.0      # Richardson: O(h^4)
+            got = out[1 + nv + idx]
+            assert np.abs(got - fd).max() < 2e-5 * np.abs(fd).max() + 2e-9, (a, b)
+            idx += 1
