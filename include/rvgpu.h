@@ -77,7 +77,8 @@ int rv_model_set_option(rv_model* model, const char* key, double value);
 int rv_loglik(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, const double* theta, int64_t W,
               double* logp, int32_t* status);
 
-/* Same with DEVICE buffers, asynchronous on `stream` (a cudaStream_t; NULL = the context's stream). */
+/* Same with DEVICE buffers, asynchronous on `stream` (a cudaStream_t; NULL = the legacy default stream,
+ * rv_ctx_stream() = the context's own).  The context's scratch is reused: one call in flight per context. */
 int rv_loglik_dev(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, const double* d_theta, int64_t W,
                   double* d_logp, int32_t* d_status, void* stream);
 
@@ -94,6 +95,7 @@ int rv_count_work(rv_ctx* ctx, int enable);     /* off by default (atomics per i
 int rv_fp64_peak(rv_ctx* ctx, double* tflops);
 
 int rv_sync(rv_ctx* ctx);
+void* rv_ctx_stream(rv_ctx* ctx);   /* the context's cudaStream_t */
 
 #ifdef __cplusplus
 }

@@ -52,6 +52,7 @@ _SIGNATURES = {
     "rv_count_work": (C.c_int, [C.c_void_p, C.c_int]),
     "rv_fp64_peak": (C.c_int, [C.c_void_p, _dp]),
     "rv_sync": (C.c_int, [C.c_void_p]),
+    "rv_ctx_stream": (C.c_void_p, [C.c_void_p]),
 }
 
 
@@ -169,12 +170,18 @@ class ModelHandle(object):
                                           float(hill_factor), int(dims), C.byref(h)), "rv_model_create")
         self.h = h
 
+    def _theta(self, theta):
+        theta = np.asarray(theta, dtype=np.float64)
+        if self.nvars == 0:       # every element pinned: only the walker count matters
+            return np.zeros((theta.shape[0] if theta.ndim >= 1 else 1, 0))
+        return np.ascontiguousarray(theta.reshape(-1, self.nvars))
+
     def set_option(self, key, value):
         self.ctx.check(self.ctx.lib.rv_model_set_option(self.h, key.encode(), float(value)), "rv_model_set_option")
 
     def loglik(self, obs, theta):
         """theta[W][nvars] (host) -> (logp[W], status[W]); State.get_logp for a batch."""
-        theta = _f64(theta).reshape(-1, max(self.nvars, 1)) if self.nvars else _f64(theta).reshape(-1, 0)
+        theta = self._theta(theta)
         W = theta.shape[0]
         logp = np.empty(W, dtype=np.float64)
         status = np.empty(W, dtype=np.int32)
@@ -183,14 +190,17 @@ class ModelHandle(object):
         return logp, status
 
     def loglik_dev(self, obs, d_theta, W, d_logp, d_status, stream=None):
-        """Device-pointer variant (ints from torch .data_ptr()), asynchronous on `stream`."""
+        """Device-pointer variant (ints from torch .data_ptr()), asynchronous on `stream` (a raw cudaStream_t
+        value, e.g. torch.cuda.current_stream().cuda_stream; None = the context's own stream)."""
+        if stream is None:
+            stream = self.ctx.lib.rv_ctx_stream(self.ctx.h)
         self.ctx.check(self.ctx.lib.rv_loglik_dev(self.ctx.h, self.h, obs.h, C.c_void_p(d_theta), int(W),
                                                   C.c_void_p(d_logp), C.c_void_p(d_status),
                                                   C.c_void_p(stream) if stream else None), "rv_loglik_dev")
 
     def rv_curve(self, theta, times):
         """theta[W][nvars], times[nt] -> (rv[W][nt], status[W]); State.get_rv for a batch."""
-        theta = _f64(theta).reshape(-1, max(self.nvars, 1)) if self.nvars else _f64(theta).reshape(-1, 0)
+        theta = self._theta(theta)
         times = _f64(times)
         W, nt = theta.shape[0], len(times)
         rv = np.zeros((W, nt), dtype=np.float64)

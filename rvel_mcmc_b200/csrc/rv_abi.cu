@@ -220,7 +220,7 @@ int rv_loglik_dev(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, const d
     if (!ctx || !model || !obs) return fail(ctx, -1, "rv_loglik_dev: NULL handle");
     if (W < 0) return fail(ctx, -2, "rv_loglik_dev: negative W");
     CU(ctx, cudaSetDevice(ctx->device));
-    return loglik_dev_impl(ctx, model, obs, d_theta, W, d_logp, d_status, stream ? (cudaStream_t)stream : ctx->stream);
+    return loglik_dev_impl(ctx, model, obs, d_theta, W, d_logp, d_status, (cudaStream_t)stream);
 }
 
 int rv_loglik(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, const double* theta, int64_t W,
@@ -320,6 +320,8 @@ int rv_fp64_peak(rv_ctx* ctx, double* tflops) {
     *tflops = best;
     return 0;
 }
+
+void* rv_ctx_stream(rv_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
 int rv_sync(rv_ctx* ctx) {
     if (!ctx) return -1;
