@@ -87,6 +87,36 @@ int rv_loglik_dev(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, const d
 int rv_rv_curve(rv_ctx* ctx, const rv_model* model, const double* theta, int64_t W, const double* times,
                 int nt, double* rv, int32_t* status);
 
+/* ---- Mh.step (mcmc.py:107-121) for W independent chains, nsteps steps, device-resident ---------- */
+/* theta[W][nvars], logp[W]: start state in, final state out (have_logp = 0: logp is computed first, as
+ * Mh.step's state.get_logp).  Proposal = theta + step_size*scales*z (mcmc.py:89-93); a proposal that fails
+ * priorHard or raises Encounter is rejected (mcmc.py:112,119).  RNG: Philox-4x32-10 keyed by
+ * (seed, first_chain_id + w, first_step + s) -- independent of sharding.  Optional outputs (NULL to skip):
+ * chain[nsteps/thin][W][nvars] and chain_logp[nsteps/thin][W] (state after every thin-th step),
+ * n_accept[W], accepted[nsteps][W].                                                                     */
+int rv_mh_run(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, double* theta, double* logp, int have_logp,
+              const double* scales, double step_size, uint64_t seed, uint64_t first_chain_id, uint32_t first_step,
+              int nsteps, int thin, int64_t W, double* chain, double* chain_logp, uint64_t* n_accept,
+              uint8_t* accepted);
+
+/* ---- Ensemble.step (mcmc.py:57-65): emcee-2.2.1 affine stretch move, W walkers (even), nsteps steps ---- */
+/* Each step = two half-steps (first half against the second, then the reverse).  lnp[W] as logp above.
+ * walker ids for the RNG are the ensemble indices 0..W-1.  Same optional outputs as rv_mh_run.          */
+int rv_stretch_run(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, double* theta, double* lnp, int have_lnp,
+                   double a, uint64_t seed, uint32_t first_step, int nsteps, int thin, int64_t W, double* chain,
+                   double* chain_lnp, uint64_t* n_accept, uint8_t* accepted);
+
+/* One half-step on DEVICE buffers for walker shards (multi-GPU): updates d_S[nS] (global ids id0_S..) in place
+ * against the complementary half d_C[nC]; the caller all-gathers the updated half afterwards.             */
+int rv_stretch_half_dev(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, double* d_S, int64_t nS,
+                        uint64_t id0_S, const double* d_C, int64_t nC, double* d_lnp_S, double a, uint64_t seed,
+                        uint32_t step, uint32_t half, uint64_t* d_n_accept, uint8_t* d_accepted, void* stream);
+
+/* nsteps MH steps on DEVICE buffers (chains sharded over GPUs need no exchange). */
+int rv_mh_steps_dev(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, double* d_theta, double* d_logp,
+                    const double* d_scales, double step_size, uint64_t seed, uint64_t first_chain_id,
+                    uint32_t first_step, int nsteps, int64_t W, uint64_t* d_n_accept, void* stream);
+
 /* ---- work accounting: force evaluations and IAS15 step attempts since the last reset ----------- */
 int rv_work_counters(rv_ctx* ctx, uint64_t out[2], int reset);
 int rv_count_work(rv_ctx* ctx, int enable);     /* off by default (atomics per item when on)       */

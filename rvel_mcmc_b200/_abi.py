@@ -48,6 +48,17 @@ _SIGNATURES = {
                                 C.c_void_p]),
     "rv_rv_curve": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p,
                               C.c_void_p]),
+    "rv_mh_run": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_double,
+                            C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p,
+                            C.c_void_p, C.c_void_p]),
+    "rv_stretch_run": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double,
+                                 C.c_uint64, C.c_uint32, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_void_p]),
+    "rv_stretch_half_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_uint64, C.c_void_p,
+                                      C.c_int64, C.c_void_p, C.c_double, C.c_uint64, C.c_uint32, C.c_uint32,
+                                      C.c_void_p, C.c_void_p, C.c_void_p]),
+    "rv_mh_steps_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
+                                  C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]),
     "rv_work_counters": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.c_int]),
     "rv_count_work": (C.c_int, [C.c_void_p, C.c_int]),
     "rv_fp64_peak": (C.c_int, [C.c_void_p, _dp]),
@@ -208,6 +219,64 @@ class ModelHandle(object):
         self.ctx.check(self.ctx.lib.rv_rv_curve(self.ctx.h, self.h, _ptr(theta), W, _ptr(times), nt, _ptr(rv),
                                                 _ptr(status)), "rv_rv_curve")
         return rv, status
+
+    # ---- fused device samplers -------------------------------------------------------------------
+    def mh_run(self, obs, theta, scales, step_size, nsteps, seed=0, first_chain_id=0, first_step=0, thin=1,
+               logp=None, record_chain=True, record_accepts=False):
+        """W independent Metropolis-Hastings chains (Mh.step, mcmc.py:107-121) run on the device.
+        Returns dict(theta, logp, chain[nsteps//thin][W][nvars], chain_logp, n_accept[W], accepted[nsteps][W])."""
+        theta = self._theta(theta).copy()
+        W = theta.shape[0]
+        have = logp is not None
+        lp = _f64(logp).copy() if have else np.zeros(W)
+        scales = _f64(scales)
+        rows = nsteps // thin
+        chain = np.zeros((rows, W, self.nvars)) if record_chain else None
+        chain_lp = np.zeros((rows, W)) if record_chain else None
+        nacc = np.zeros(W, dtype=np.uint64)
+        acc = np.zeros((nsteps, W), dtype=np.uint8) if record_accepts else None
+        self.ctx.check(self.ctx.lib.rv_mh_run(self.ctx.h, self.h, obs.h, _ptr(theta), _ptr(lp), 1 if have else 0,
+                                              _ptr(scales), float(step_size), int(seed), int(first_chain_id),
+                                              int(first_step), int(nsteps), int(thin), W, _ptr(chain), _ptr(chain_lp),
+                                              _ptr(nacc), _ptr(acc)), "rv_mh_run")
+        return dict(theta=theta, logp=lp, chain=chain, chain_logp=chain_lp, n_accept=nacc, accepted=acc)
+
+    def stretch_run(self, obs, theta, nsteps, a=2.0, seed=0, first_step=0, thin=1, lnp=None, record_chain=True,
+                    record_accepts=False):
+        """Affine stretch ensemble (Ensemble.step, mcmc.py:57-65; emcee 2.2.1 move) run on the device."""
+        theta = self._theta(theta).copy()
+        W = theta.shape[0]
+        have = lnp is not None
+        lp = _f64(lnp).copy() if have else np.zeros(W)
+        rows = nsteps // thin
+        chain = np.zeros((rows, W, self.nvars)) if record_chain else None
+        chain_lp = np.zeros((rows, W)) if record_chain else None
+        nacc = np.zeros(W, dtype=np.uint64)
+        acc = np.zeros((nsteps, W), dtype=np.uint8) if record_accepts else None
+        self.ctx.check(self.ctx.lib.rv_stretch_run(self.ctx.h, self.h, obs.h, _ptr(theta), _ptr(lp), 1 if have else 0,
+                                                   float(a), int(seed), int(first_step), int(nsteps), int(thin), W,
+                                                   _ptr(chain), _ptr(chain_lp), _ptr(nacc), _ptr(acc)), "rv_stretch_run")
+        return dict(theta=theta, lnp=lp, chain=chain, chain_lnp=chain_lp, n_accept=nacc, accepted=acc)
+
+    def stretch_half_dev(self, obs, d_S, nS, id0_S, d_C, nC, d_lnp_S, a, seed, step, half, d_n_accept=0, d_accepted=0,
+                         stream=None):
+        if stream is None:
+            stream = self.ctx.lib.rv_ctx_stream(self.ctx.h)
+        self.ctx.check(self.ctx.lib.rv_stretch_half_dev(self.ctx.h, self.h, obs.h, C.c_void_p(d_S), int(nS), int(id0_S),
+                                                        C.c_void_p(d_C), int(nC), C.c_void_p(d_lnp_S), float(a), int(seed),
+                                                        int(step), int(half), C.c_void_p(d_n_accept) if d_n_accept else None,
+                                                        C.c_void_p(d_accepted) if d_accepted else None,
+                                                        C.c_void_p(stream) if stream else None), "rv_stretch_half_dev")
+
+    def mh_steps_dev(self, obs, d_theta, d_logp, d_scales, step_size, seed, first_chain_id, first_step, nsteps, W,
+                     d_n_accept=0, stream=None):
+        if stream is None:
+            stream = self.ctx.lib.rv_ctx_stream(self.ctx.h)
+        self.ctx.check(self.ctx.lib.rv_mh_steps_dev(self.ctx.h, self.h, obs.h, C.c_void_p(d_theta), C.c_void_p(d_logp),
+                                                    C.c_void_p(d_scales), float(step_size), int(seed), int(first_chain_id),
+                                                    int(first_step), int(nsteps), int(W),
+                                                    C.c_void_p(d_n_accept) if d_n_accept else None,
+                                                    C.c_void_p(stream) if stream else None), "rv_mh_steps_dev")
 
     def close(self):
         if getattr(self, "h", None):

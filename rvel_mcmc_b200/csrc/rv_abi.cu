@@ -24,6 +24,15 @@ struct rv_ctx {
     int* d_pstat; size_t cap_pstat;
     double* d_times; size_t cap_times;
     double* d_rv; size_t cap_rv;
+    double* d_prop; size_t cap_prop;
+    double* d_plogp; size_t cap_plogp;
+    int* d_pstatus; size_t cap_pstatus;
+    double* d_zz; size_t cap_zz;
+    double* d_scales; size_t cap_scales;
+    double* d_chain; size_t cap_chain;
+    double* d_chainlp; size_t cap_chainlp;
+    unsigned long long* d_nacc; size_t cap_nacc;
+    unsigned char* d_acc; size_t cap_acc;
     char err[512];
 };
 struct rv_obs {
@@ -111,6 +120,8 @@ int rv_ctx_destroy(rv_ctx* c) {
     cudaFree(c->d_item_counter); cudaFree(c->d_work);
     cudaFree(c->d_theta); cudaFree(c->d_logp); cudaFree(c->d_status); cudaFree(c->d_part);
     cudaFree(c->d_pstat); cudaFree(c->d_times); cudaFree(c->d_rv);
+    cudaFree(c->d_prop); cudaFree(c->d_plogp); cudaFree(c->d_pstatus); cudaFree(c->d_zz); cudaFree(c->d_scales);
+    cudaFree(c->d_chain); cudaFree(c->d_chainlp); cudaFree(c->d_nacc); cudaFree(c->d_acc);
     cudaStreamDestroy(c->stream);
     delete c;
     return 0;
@@ -272,6 +283,172 @@ int rv_rv_curve(rv_ctx* ctx, const rv_model* model, const double* theta, int64_t
     CU(ctx, rv::launch_curve_finalize(ctx->d_item_counter, s));
     if (nt) CU(ctx, cudaMemcpyAsync(rv, ctx->d_rv, (size_t)W * nt * sizeof(double), cudaMemcpyDeviceToHost, s));
     CU(ctx, cudaMemcpyAsync(status, ctx->d_pstat, (size_t)W * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    CU(ctx, cudaStreamSynchronize(s));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// samplers
+
+static int mh_steps_impl(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, double* d_theta, double* d_logp,
+                         const double* d_scales, double step_size, uint64_t seed, uint64_t first_id, uint32_t first_step,
+                         int nsteps, int thin, int64_t W, unsigned long long* d_nacc, unsigned char* d_acc_rows,
+                         double* d_chain, double* d_chainlp, cudaStream_t s) {
+    const int nv = model->h.nvars;
+    if (int rc = ensure(ctx, &ctx->d_prop, &ctx->cap_prop, (size_t)W * (nv > 0 ? nv : 1))) return rc;
+    if (int rc = ensure(ctx, &ctx->d_plogp, &ctx->cap_plogp, (size_t)W)) return rc;
+    if (int rc = ensure(ctx, &ctx->d_pstatus, &ctx->cap_pstatus, (size_t)W)) return rc;
+    long long row = 0;
+    for (int k = 0; k < nsteps; k++) {
+        const unsigned step = first_step + (unsigned)k;
+        CU(ctx, rv::launch_mh_propose(d_theta, d_scales, step_size, nv, W, seed, first_id, step, ctx->d_prop, s));
+        if (int rc = loglik_dev_impl(ctx, model, obs, ctx->d_prop, W, ctx->d_plogp, ctx->d_pstatus, s)) return rc;
+        const bool rec = d_chain && thin > 0 && ((k + 1) % thin == 0);
+        CU(ctx, rv::launch_mh_accept(d_theta, d_logp, ctx->d_prop, ctx->d_plogp, ctx->d_pstatus, nv, W, seed, first_id, step,
+                                     d_nacc, d_acc_rows ? d_acc_rows + (size_t)k * W : nullptr,
+                                     rec ? d_chain + (size_t)row * W * nv : nullptr,
+                                     rec ? d_chainlp + (size_t)row * W : nullptr, s));
+        if (rec) row++;
+    }
+    return 0;
+}
+
+int rv_mh_steps_dev(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, double* d_theta, double* d_logp,
+                    const double* d_scales, double step_size, uint64_t seed, uint64_t first_chain_id,
+                    uint32_t first_step, int nsteps, int64_t W, uint64_t* d_n_accept, void* stream) {
+    if (!ctx || !model || !obs) return fail(ctx, -1, "rv_mh_steps_dev: NULL handle");
+    if (W <= 0 || nsteps < 0) return fail(ctx, -2, "rv_mh_steps_dev: bad size");
+    CU(ctx, cudaSetDevice(ctx->device));
+    return mh_steps_impl(ctx, model, obs, d_theta, d_logp, d_scales, step_size, seed, first_chain_id, first_step, nsteps, 0,
+                         W, (unsigned long long*)d_n_accept, nullptr, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int rv_mh_run(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, double* theta, double* logp, int have_logp,
+              const double* scales, double step_size, uint64_t seed, uint64_t first_chain_id, uint32_t first_step,
+              int nsteps, int thin, int64_t W, double* chain, double* chain_logp, uint64_t* n_accept,
+              uint8_t* accepted) {
+    if (!ctx || !model || !obs || !theta || !logp || !scales) return fail(ctx, -1, "rv_mh_run: NULL argument");
+    if (W <= 0 || nsteps < 0) return fail(ctx, -2, "rv_mh_run: bad size");
+    if (thin < 1) thin = 1;
+    CU(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const int nv = model->h.nvars;
+    const size_t nvs = (size_t)(nv > 0 ? nv : 1);
+    const long long rows = chain ? nsteps / thin : 0;
+    if (int rc = ensure(ctx, &ctx->d_theta, &ctx->cap_theta, (size_t)W * nvs)) return rc;
+    if (int rc = ensure(ctx, &ctx->d_logp, &ctx->cap_logp, (size_t)W)) return rc;
+    if (int rc = ensure(ctx, &ctx->d_status, &ctx->cap_status, (size_t)W)) return rc;
+    if (int rc = ensure(ctx, &ctx->d_scales, &ctx->cap_scales, nvs)) return rc;
+    if (int rc = ensure(ctx, &ctx->d_nacc, &ctx->cap_nacc, (size_t)W)) return rc;
+    if (rows) {
+        if (int rc = ensure(ctx, &ctx->d_chain, &ctx->cap_chain, (size_t)rows * W * nvs)) return rc;
+        if (int rc = ensure(ctx, &ctx->d_chainlp, &ctx->cap_chainlp, (size_t)rows * W)) return rc;
+    }
+    if (accepted) if (int rc = ensure(ctx, &ctx->d_acc, &ctx->cap_acc, (size_t)nsteps * W + 1)) return rc;
+    CU(ctx, cudaMemcpyAsync(ctx->d_theta, theta, (size_t)W * nv * sizeof(double), cudaMemcpyHostToDevice, s));
+    CU(ctx, cudaMemcpyAsync(ctx->d_scales, scales, (size_t)nv * sizeof(double), cudaMemcpyHostToDevice, s));
+    CU(ctx, cudaMemsetAsync(ctx->d_nacc, 0, (size_t)W * sizeof(unsigned long long), s));
+    if (have_logp) {
+        CU(ctx, cudaMemcpyAsync(ctx->d_logp, logp, (size_t)W * sizeof(double), cudaMemcpyHostToDevice, s));
+    } else {
+        if (int rc = loglik_dev_impl(ctx, model, obs, ctx->d_theta, W, ctx->d_logp, ctx->d_status, s)) return rc;
+        CU(ctx, rv::launch_mask_logp(ctx->d_logp, ctx->d_status, W, s));
+    }
+    if (int rc = mh_steps_impl(ctx, model, obs, ctx->d_theta, ctx->d_logp, ctx->d_scales, step_size, seed, first_chain_id,
+                               first_step, nsteps, thin, W, ctx->d_nacc, accepted ? ctx->d_acc : nullptr,
+                               rows ? ctx->d_chain : nullptr, rows ? ctx->d_chainlp : nullptr, s)) return rc;
+    CU(ctx, cudaMemcpyAsync(theta, ctx->d_theta, (size_t)W * nv * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CU(ctx, cudaMemcpyAsync(logp, ctx->d_logp, (size_t)W * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (rows) {
+        CU(ctx, cudaMemcpyAsync(chain, ctx->d_chain, (size_t)rows * W * nv * sizeof(double), cudaMemcpyDeviceToHost, s));
+        if (chain_logp) CU(ctx, cudaMemcpyAsync(chain_logp, ctx->d_chainlp, (size_t)rows * W * sizeof(double), cudaMemcpyDeviceToHost, s));
+    }
+    if (n_accept) CU(ctx, cudaMemcpyAsync(n_accept, ctx->d_nacc, (size_t)W * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    if (accepted) CU(ctx, cudaMemcpyAsync(accepted, ctx->d_acc, (size_t)nsteps * W, cudaMemcpyDeviceToHost, s));
+    CU(ctx, cudaStreamSynchronize(s));
+    return 0;
+}
+
+static int stretch_half_impl(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, double* d_S, int64_t nS,
+                             uint64_t id0_S, const double* d_C, int64_t nC, double* d_lnp_S, double a, uint64_t seed,
+                             uint32_t step, uint32_t half, unsigned long long* d_nacc, unsigned char* d_acc,
+                             cudaStream_t s) {
+    const int nv = model->h.nvars;
+    if (int rc = ensure(ctx, &ctx->d_prop, &ctx->cap_prop, (size_t)nS * (nv > 0 ? nv : 1))) return rc;
+    if (int rc = ensure(ctx, &ctx->d_plogp, &ctx->cap_plogp, (size_t)nS)) return rc;
+    if (int rc = ensure(ctx, &ctx->d_pstatus, &ctx->cap_pstatus, (size_t)nS)) return rc;
+    if (int rc = ensure(ctx, &ctx->d_zz, &ctx->cap_zz, (size_t)nS)) return rc;
+    CU(ctx, rv::launch_stretch_propose(d_S, d_C, nv, nS, nC, a, seed, id0_S, step, half, ctx->d_prop, ctx->d_zz, s));
+    if (int rc = loglik_dev_impl(ctx, model, obs, ctx->d_prop, nS, ctx->d_plogp, ctx->d_pstatus, s)) return rc;
+    CU(ctx, rv::launch_stretch_accept(d_S, d_lnp_S, ctx->d_prop, ctx->d_plogp, ctx->d_pstatus, ctx->d_zz, nv, nS, seed, id0_S,
+                                      step, half, d_nacc, d_acc, s));
+    return 0;
+}
+
+int rv_stretch_half_dev(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, double* d_S, int64_t nS,
+                        uint64_t id0_S, const double* d_C, int64_t nC, double* d_lnp_S, double a, uint64_t seed,
+                        uint32_t step, uint32_t half, uint64_t* d_n_accept, uint8_t* d_accepted, void* stream) {
+    if (!ctx || !model || !obs) return fail(ctx, -1, "rv_stretch_half_dev: NULL handle");
+    if (nS <= 0 || nC <= 0) return fail(ctx, -2, "rv_stretch_half_dev: empty half");
+    CU(ctx, cudaSetDevice(ctx->device));
+    return stretch_half_impl(ctx, model, obs, d_S, nS, id0_S, d_C, nC, d_lnp_S, a, seed, step, half,
+                             (unsigned long long*)d_n_accept, d_accepted, (cudaStream_t)stream);
+}
+
+int rv_stretch_run(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, double* theta, double* lnp, int have_lnp,
+                   double a, uint64_t seed, uint32_t first_step, int nsteps, int thin, int64_t W, double* chain,
+                   double* chain_lnp, uint64_t* n_accept, uint8_t* accepted) {
+    if (!ctx || !model || !obs || !theta || !lnp) return fail(ctx, -1, "rv_stretch_run: NULL argument");
+    if (W < 2 || (W & 1)) return fail(ctx, -2, "rv_stretch_run: the number of walkers must be even (emcee asserts the same)");
+    if (nsteps < 0) return fail(ctx, -2, "rv_stretch_run: negative nsteps");
+    if (thin < 1) thin = 1;
+    CU(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const int nv = model->h.nvars;
+    const size_t nvs = (size_t)(nv > 0 ? nv : 1);
+    const long long rows = chain ? nsteps / thin : 0;
+    const int64_t h = W / 2;
+    if (int rc = ensure(ctx, &ctx->d_theta, &ctx->cap_theta, (size_t)W * nvs)) return rc;
+    if (int rc = ensure(ctx, &ctx->d_logp, &ctx->cap_logp, (size_t)W)) return rc;
+    if (int rc = ensure(ctx, &ctx->d_status, &ctx->cap_status, (size_t)W)) return rc;
+    if (int rc = ensure(ctx, &ctx->d_nacc, &ctx->cap_nacc, (size_t)W)) return rc;
+    if (rows) {
+        if (int rc = ensure(ctx, &ctx->d_chain, &ctx->cap_chain, (size_t)rows * W * nvs)) return rc;
+        if (int rc = ensure(ctx, &ctx->d_chainlp, &ctx->cap_chainlp, (size_t)rows * W)) return rc;
+    }
+    if (accepted) if (int rc = ensure(ctx, &ctx->d_acc, &ctx->cap_acc, (size_t)nsteps * W + 1)) return rc;
+    CU(ctx, cudaMemcpyAsync(ctx->d_theta, theta, (size_t)W * nv * sizeof(double), cudaMemcpyHostToDevice, s));
+    CU(ctx, cudaMemsetAsync(ctx->d_nacc, 0, (size_t)W * sizeof(unsigned long long), s));
+    if (have_lnp) {
+        CU(ctx, cudaMemcpyAsync(ctx->d_logp, lnp, (size_t)W * sizeof(double), cudaMemcpyHostToDevice, s));
+    } else {
+        if (int rc = loglik_dev_impl(ctx, model, obs, ctx->d_theta, W, ctx->d_logp, ctx->d_status, s)) return rc;
+        CU(ctx, rv::launch_mask_logp(ctx->d_logp, ctx->d_status, W, s));
+    }
+    long long row = 0;
+    for (int k = 0; k < nsteps; k++) {
+        const unsigned step = first_step + (unsigned)k;
+        for (unsigned half = 0; half < 2; half++) {
+            double* S = ctx->d_theta + (half == 0 ? 0 : (size_t)h * nv);
+            const double* C = ctx->d_theta + (half == 0 ? (size_t)h * nv : 0);
+            const uint64_t id0 = half == 0 ? 0 : (uint64_t)h;
+            if (int rc = stretch_half_impl(ctx, model, obs, S, h, id0, C, h, ctx->d_logp + id0, a, seed, step, half,
+                                           ctx->d_nacc + id0, accepted ? ctx->d_acc + (size_t)k * W + id0 : nullptr, s)) return rc;
+        }
+        if (rows && ((k + 1) % thin == 0)) {
+            CU(ctx, cudaMemcpyAsync(ctx->d_chain + (size_t)row * W * nv, ctx->d_theta, (size_t)W * nv * sizeof(double), cudaMemcpyDeviceToDevice, s));
+            CU(ctx, cudaMemcpyAsync(ctx->d_chainlp + (size_t)row * W, ctx->d_logp, (size_t)W * sizeof(double), cudaMemcpyDeviceToDevice, s));
+            row++;
+        }
+    }
+    CU(ctx, cudaMemcpyAsync(theta, ctx->d_theta, (size_t)W * nv * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CU(ctx, cudaMemcpyAsync(lnp, ctx->d_logp, (size_t)W * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (rows) {
+        CU(ctx, cudaMemcpyAsync(chain, ctx->d_chain, (size_t)rows * W * nv * sizeof(double), cudaMemcpyDeviceToHost, s));
+        if (chain_lnp) CU(ctx, cudaMemcpyAsync(chain_lnp, ctx->d_chainlp, (size_t)rows * W * sizeof(double), cudaMemcpyDeviceToHost, s));
+    }
+    if (n_accept) CU(ctx, cudaMemcpyAsync(n_accept, ctx->d_nacc, (size_t)W * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    if (accepted) CU(ctx, cudaMemcpyAsync(accepted, ctx->d_acc, (size_t)nsteps * W, cudaMemcpyDeviceToHost, s));
     CU(ctx, cudaStreamSynchronize(s));
     return 0;
 }

@@ -8,4 +8,20 @@ cudaError_t launch_finalize(const double* part_chi2, const int* part_status, lon
                             double* logp, int* status, unsigned long long* item_counter, cudaStream_t stream);
 cudaError_t launch_curve_finalize(unsigned long long* item_counter, cudaStream_t stream);
 cudaError_t launch_fp64_peak(double* d_out, int blocks, int iters, cudaStream_t stream);
+// samplers (rv_samplers.cu)
+cudaError_t launch_mh_propose(const double* theta, const double* scales, double step_size, int nvars, long long W,
+                              unsigned long long seed, unsigned long long first_id, unsigned step, double* prop,
+                              cudaStream_t s);
+cudaError_t launch_mh_accept(double* theta, double* logp, const double* prop, const double* prop_logp,
+                             const int* prop_status, int nvars, long long W, unsigned long long seed,
+                             unsigned long long first_id, unsigned step, unsigned long long* n_accept,
+                             unsigned char* accepted, double* chain_row, double* chain_logp_row, cudaStream_t s);
+cudaError_t launch_stretch_propose(const double* S, const double* C, int nvars, long long nS, long long nC, double a,
+                                   unsigned long long seed, unsigned long long id0_S, unsigned step, unsigned half,
+                                   double* q, double* zz, cudaStream_t s);
+cudaError_t launch_stretch_accept(double* S, double* lnp, const double* q, const double* q_lnp, const int* q_status,
+                                  const double* zz, int nvars, long long nS, unsigned long long seed,
+                                  unsigned long long id0_S, unsigned step, unsigned half, unsigned long long* n_accept,
+                                  unsigned char* accepted, cudaStream_t s);
+cudaError_t launch_mask_logp(double* logp, const int* status, long long W, cudaStream_t s);
 }  // namespace rv
