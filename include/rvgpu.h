@@ -69,7 +69,8 @@ int rv_obs_destroy(rv_obs* obs);
 int rv_model_create(rv_ctx* ctx, int n_planets, const double* fixed, int nvars, const int32_t* free_planet,
                     const int32_t* free_elem, double hill_factor, int dims, rv_model** out);
 int rv_model_destroy(rv_model* model);
-/* options: "dt0" (1e-3), "epsilon" (1e-9), "max_attempts", "mapping" (0 lane-per-planet, 1 thread-per-walker) */
+/* options: "dt0" (1e-3), "epsilon" (1e-9), "max_attempts", "hill_factor", "mapping" (0 lane-per-planet, 1 thread-per-walker),
+ * "check_prior" (1; 0 = rv_loglik_d_dd integrates even outside the hard prior, as state.py:290 does)        */
 int rv_model_set_option(rv_model* model, const char* key, double value);
 
 /* ---- State.get_logp (state.py:103-110) for W parameter vectors; HOST buffers -------------------- */
@@ -86,6 +87,16 @@ int rv_loglik_dev(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, const d
 /* rv[W][nt]; status[W]; no prior test (as the reference).  HOST buffers.                          */
 int rv_rv_curve(rv_ctx* ctx, const rv_model* model, const double* theta, int64_t W, const double* times,
                 int nt, double* rv, int32_t* status);
+
+/* ---- State.get_logp_d_dd (state.py:290-294; setup_sim_vars state.py:229-248, get_chi2_d_dd state.py:253-285) ---- */
+/* theta[W][nvars] -> logp[W], grad[W][nvars], hess[W][nvars][nvars] (symmetric), status[W].  The hard prior is tested
+ * first (status RV_PRIOR), as the reference's callers do (mcmc.py:171).  On a non-zero status logp = -inf and the
+ * walker's grad / hess rows are zero.  Returns -30 when the model needs more than 448 (set, planet) threads.       */
+int rv_loglik_d_dd(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, const double* theta, int64_t W,
+                   double* logp, double* grad, double* hess, int32_t* status);
+/* Same with DEVICE buffers, asynchronous on `stream`. */
+int rv_loglik_d_dd_dev(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, const double* d_theta, int64_t W,
+                       double* d_logp, double* d_grad, double* d_hess, int32_t* d_status, void* stream);
 
 /* ---- Mh.step (mcmc.py:107-121) for W independent chains, nsteps steps, device-resident ---------- */
 /* theta[W][nvars], logp[W]: start state in, final state out (have_logp = 0: logp is computed first, as

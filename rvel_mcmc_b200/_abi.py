@@ -46,6 +46,10 @@ _SIGNATURES = {
     "rv_loglik": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "rv_loglik_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                 C.c_void_p]),
+    "rv_loglik_d_dd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_void_p]),
+    "rv_loglik_d_dd_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_void_p]),
     "rv_rv_curve": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p,
                               C.c_void_p]),
     "rv_mh_run": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_double,
@@ -208,6 +212,30 @@ class ModelHandle(object):
         self.ctx.check(self.ctx.lib.rv_loglik_dev(self.ctx.h, self.h, obs.h, C.c_void_p(d_theta), int(W),
                                                   C.c_void_p(d_logp), C.c_void_p(d_status),
                                                   C.c_void_p(stream) if stream else None), "rv_loglik_dev")
+
+    def loglik_d_dd(self, obs, theta, check_prior=True):
+        """theta[W][nvars] (host) -> (logp[W], grad[W][nvars], hess[W][nvars][nvars], status[W]);
+        State.get_logp_d_dd for a batch (state.py:290-294)."""
+        theta = self._theta(theta)
+        W = theta.shape[0]
+        logp = np.empty(W, dtype=np.float64)
+        grad = np.zeros((W, self.nvars), dtype=np.float64)
+        hess = np.zeros((W, self.nvars, self.nvars), dtype=np.float64)
+        status = np.empty(W, dtype=np.int32)
+        if bool(check_prior) != getattr(self, "_check_prior", True):
+            self.set_option("check_prior", 1.0 if check_prior else 0.0)
+            self._check_prior = bool(check_prior)
+        self.ctx.check(self.ctx.lib.rv_loglik_d_dd(self.ctx.h, self.h, obs.h, _ptr(theta), W, _ptr(logp), _ptr(grad),
+                                                   _ptr(hess), _ptr(status)), "rv_loglik_d_dd")
+        return logp, grad, hess, status
+
+    def loglik_d_dd_dev(self, obs, d_theta, W, d_logp, d_grad, d_hess, d_status, stream=None):
+        if stream is None:
+            stream = self.ctx.lib.rv_ctx_stream(self.ctx.h)
+        self.ctx.check(self.ctx.lib.rv_loglik_d_dd_dev(self.ctx.h, self.h, obs.h, C.c_void_p(d_theta), int(W),
+                                                       C.c_void_p(d_logp), C.c_void_p(d_grad), C.c_void_p(d_hess),
+                                                       C.c_void_p(d_status), C.c_void_p(stream) if stream else None),
+                       "rv_loglik_d_dd_dev")
 
     def rv_curve(self, theta, times):
         """theta[W][nvars], times[nt] -> (rv[W][nt], status[W]); State.get_rv for a batch."""

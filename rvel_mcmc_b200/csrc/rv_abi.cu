@@ -8,6 +8,7 @@
 #include "rv_launch.h"
 #include "rv_loglik.cuh"
 #include "rv_model.h"
+#include "rv_var.cuh"
 
 struct rv_ctx {
     int device;
@@ -33,6 +34,9 @@ struct rv_ctx {
     double* d_chainlp; size_t cap_chainlp;
     unsigned long long* d_nacc; size_t cap_nacc;
     unsigned char* d_acc; size_t cap_acc;
+    double* d_vpart; size_t cap_vpart;
+    double* d_grad; size_t cap_grad;
+    double* d_hess; size_t cap_hess;
     char err[512];
 };
 struct rv_obs {
@@ -122,6 +126,7 @@ int rv_ctx_destroy(rv_ctx* c) {
     cudaFree(c->d_pstat); cudaFree(c->d_times); cudaFree(c->d_rv);
     cudaFree(c->d_prop); cudaFree(c->d_plogp); cudaFree(c->d_pstatus); cudaFree(c->d_zz); cudaFree(c->d_scales);
     cudaFree(c->d_chain); cudaFree(c->d_chainlp); cudaFree(c->d_nacc); cudaFree(c->d_acc);
+    cudaFree(c->d_vpart); cudaFree(c->d_grad); cudaFree(c->d_hess);
     cudaStreamDestroy(c->stream);
     delete c;
     return 0;
@@ -202,6 +207,7 @@ int rv_model_set_option(rv_model* m, const char* key, double value) {
     else if (!strcmp(key, "max_attempts")) m->h.max_attempts = (int)value;
     else if (!strcmp(key, "hill_factor")) m->h.hill_factor = value;
     else if (!strcmp(key, "mapping")) m->mapping = (int)value;
+    else if (!strcmp(key, "check_prior")) m->h.check_prior = value != 0.0;
     else return fail(ctx, -20, "rv_model_set_option: unknown key '%s'", key);
     CU(ctx, cudaSetDevice(ctx->device));
     CU(ctx, cudaMemcpy(m->d, &m->h, sizeof(rv::Model), cudaMemcpyHostToDevice));
@@ -283,6 +289,67 @@ int rv_rv_curve(rv_ctx* ctx, const rv_model* model, const double* theta, int64_t
     CU(ctx, rv::launch_curve_finalize(ctx->d_item_counter, s));
     if (nt) CU(ctx, cudaMemcpyAsync(rv, ctx->d_rv, (size_t)W * nt * sizeof(double), cudaMemcpyDeviceToHost, s));
     CU(ctx, cudaMemcpyAsync(status, ctx->d_pstat, (size_t)W * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    CU(ctx, cudaStreamSynchronize(s));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// value + gradient + Hessian
+
+static int var_dev_impl(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, const double* d_theta, int64_t W,
+                        double* d_logp, double* d_grad, double* d_hess, int32_t* d_status, cudaStream_t s) {
+    if (W == 0) return 0;
+    const int nv = model->h.nvars;
+    if (rv::var_threads_needed(model->h.P, nv) > 448)
+        return fail(ctx, -30, "variational kernel: %d planets x %d free parameters need %d (set, planet) threads; the limit is 448",
+                    model->h.P, nv, rv::var_threads_needed(model->h.P, nv));
+    const int nsets = rv::var_nsets(nv);
+    if (int rc = ensure(ctx, &ctx->d_vpart, &ctx->cap_vpart, (size_t)(2 * W) * nsets)) return rc;
+    if (int rc = ensure(ctx, &ctx->d_pstat, &ctx->cap_pstat, (size_t)(2 * W))) return rc;
+    rv::VarArgs a;
+    memset(&a, 0, sizeof a);
+    a.model = model->d; a.theta = d_theta; a.W = W;
+    a.ot = obs->d_t; a.orv = obs->d_rv; a.oerr = obs->d_err; a.nf = obs->nf; a.nb = obs->nb;
+    a.npoints = obs->npoints;
+    a.part = ctx->d_vpart; a.part_status = ctx->d_pstat;
+    a.item_counter = ctx->d_item_counter;
+    a.work_counters = ctx->count_work ? ctx->d_work : nullptr;
+    CU(ctx, rv::launch_var(a, model->h.P, model->h.D, nv, ctx->num_sms, s));
+    CU(ctx, rv::launch_var_finalize(ctx->d_vpart, ctx->d_pstat, W, nv, d_logp, d_grad, d_hess, d_status, ctx->d_item_counter, s));
+    return 0;
+}
+
+int rv_loglik_d_dd_dev(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, const double* d_theta, int64_t W,
+                       double* d_logp, double* d_grad, double* d_hess, int32_t* d_status, void* stream) {
+    if (!ctx || !model || !obs) return fail(ctx, -1, "rv_loglik_d_dd_dev: NULL handle");
+    if (W < 0) return fail(ctx, -2, "rv_loglik_d_dd_dev: negative W");
+    CU(ctx, cudaSetDevice(ctx->device));
+    return var_dev_impl(ctx, model, obs, d_theta, W, d_logp, d_grad, d_hess, d_status, (cudaStream_t)stream);
+}
+
+int rv_loglik_d_dd(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, const double* theta, int64_t W,
+                   double* logp, double* grad, double* hess, int32_t* status) {
+    if (!ctx || !model || !obs) return fail(ctx, -1, "rv_loglik_d_dd: NULL handle");
+    if (W < 0) return fail(ctx, -2, "rv_loglik_d_dd: negative W");
+    if (W == 0) return 0;
+    if (!theta || !logp || !grad || !hess || !status) return fail(ctx, -1, "rv_loglik_d_dd: NULL buffer");
+    CU(ctx, cudaSetDevice(ctx->device));
+    const int nv = model->h.nvars;
+    const size_t nvs = (size_t)(nv > 0 ? nv : 1);
+    if (int rc = ensure(ctx, &ctx->d_theta, &ctx->cap_theta, (size_t)W * nvs)) return rc;
+    if (int rc = ensure(ctx, &ctx->d_logp, &ctx->cap_logp, (size_t)W)) return rc;
+    if (int rc = ensure(ctx, &ctx->d_status, &ctx->cap_status, (size_t)W)) return rc;
+    if (int rc = ensure(ctx, &ctx->d_grad, &ctx->cap_grad, (size_t)W * nvs)) return rc;
+    if (int rc = ensure(ctx, &ctx->d_hess, &ctx->cap_hess, (size_t)W * nvs * nvs)) return rc;
+    cudaStream_t s = ctx->stream;
+    if (nv > 0) CU(ctx, cudaMemcpyAsync(ctx->d_theta, theta, (size_t)W * nv * sizeof(double), cudaMemcpyHostToDevice, s));
+    if (int rc = var_dev_impl(ctx, model, obs, ctx->d_theta, W, ctx->d_logp, ctx->d_grad, ctx->d_hess, ctx->d_status, s)) return rc;
+    CU(ctx, cudaMemcpyAsync(logp, ctx->d_logp, (size_t)W * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CU(ctx, cudaMemcpyAsync(status, ctx->d_status, (size_t)W * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    if (nv > 0) {
+        CU(ctx, cudaMemcpyAsync(grad, ctx->d_grad, (size_t)W * nv * sizeof(double), cudaMemcpyDeviceToHost, s));
+        CU(ctx, cudaMemcpyAsync(hess, ctx->d_hess, (size_t)W * nv * nv * sizeof(double), cudaMemcpyDeviceToHost, s));
+    }
     CU(ctx, cudaStreamSynchronize(s));
     return 0;
 }

@@ -50,6 +50,7 @@ struct Model {
     double epsilon;         // rebound default 1e-9
     double m_star;          // 1.0 (state.py:38)
     int max_attempts;       // safety bound on IAS15 step attempts per leg
+    int check_prior;        // variational entry point: test priorHard first (1, default) or integrate regardless (0)
 };
 
 RV_HD bool is_normal(double x) {

@@ -8,6 +8,12 @@ cudaError_t launch_finalize(const double* part_chi2, const int* part_status, lon
                             double* logp, int* status, unsigned long long* item_counter, cudaStream_t stream);
 cudaError_t launch_curve_finalize(unsigned long long* item_counter, cudaStream_t stream);
 cudaError_t launch_fp64_peak(double* d_out, int blocks, int iters, cudaStream_t stream);
+// variational path (rv_var_kernels.cu)
+struct VarArgs;
+int var_threads_needed(int P, int nv);
+cudaError_t launch_var(const VarArgs& a, int P, int D, int nv, int num_sms, cudaStream_t stream);
+cudaError_t launch_var_finalize(const double* part, const int* pstat, long long W, int nv, double* logp, double* grad,
+                                double* hess, int* status, unsigned long long* item_counter, cudaStream_t stream);
 // samplers (rv_samplers.cu)
 cudaError_t launch_mh_propose(const double* theta, const double* scales, double step_size, int nvars, long long W,
                               unsigned long long seed, unsigned long long first_id, unsigned step, double* prop,

@@ -39,6 +39,7 @@ inline int build_model(Model* m, int P, const double* fixed, int nvars, const in
     m->epsilon = 1e-9;
     m->m_star = 1.0;     // state.py:38
     m->max_attempts = 1 << 20;
+    m->check_prior = 1;
     return 0;
 }
 

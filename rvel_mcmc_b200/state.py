@@ -235,8 +235,17 @@ class State(object):
                 vi += 1
 
     def get_chi2_d_dd(self, obs):
-        from . import variational
-        return variational.chi2_d_dd(self, obs)
+        """state.py:253-285 -- chi2, its gradient and Hessian from one fused variational kernel evaluation
+        (real system + Nvars first-order + Nvars(Nvars+1)/2 second-order sets; forward leg, then a fresh
+        monotone backward leg).  Like the reference, no prior test here (callers do it, mcmc.py:171)."""
+        ctx = _abi.default_context()
+        model = self._model(ctx)
+        logp, grad, hess, status = model.loglik_d_dd(obs._handle(ctx), self.get_params()[None, :], check_prior=False)
+        if status[0] == _abi.RV_ENCOUNTER:
+            raise Encounter("Two particles had a close encounter (d<exit_min_distance).")
+        if status[0] != _abi.RV_OK:
+            raise _abi.RvGpuError("variational evaluation failed with status %d" % status[0])
+        return -float(logp[0]), -grad[0], -hess[0]
 
     def get_logp_d_dd(self, obs):
         if self.logp is None or self.logp_d is None:

@@ -165,3 +165,42 @@ def gaussian_ball(center, scales, W, seed, width=1e-3):
 
 HD_SCALES = {"m": 5.5e-6, "a": 0.001, "h": 0.02, "k": 0.02, "l": np.pi / 4}   # (Ex)HD155358.ipynb:456
 HD_SCALE_VEC = [HD_SCALES[k] for k in ("a", "h", "k", "m", "l")] * 2
+
+
+def orc_logp_d_dd_batch(fixed, fp, fe, hill, obs, theta, var_in_norm=0, nthreads=8):
+    """Oracle State.get_logp_d_dd for a batch: (logp[W], grad[W][nv], hess[W][nv][nv], status[W], counters)."""
+    fixed = np.ascontiguousarray(fixed, dtype=np.float64)
+    theta = np.ascontiguousarray(theta, dtype=np.float64)
+    fp = np.ascontiguousarray(fp, dtype=np.int32)
+    fe = np.ascontiguousarray(fe, dtype=np.int32)
+    W, nv = theta.shape[0], len(fp)
+    logp = np.zeros(W)
+    grad = np.zeros((W, nv))
+    hess = np.zeros((W, nv, nv))
+    status = np.zeros(W, dtype=np.int32)
+    cnt = (C.c_long * 3)()
+    oracle().orc_logp_d_dd_batch(fixed.shape[0], vp(fixed), nv, vp(fp), vp(fe), C.c_double(hill),
+                                 vp(obs.tf), vp(obs.rvf), vp(obs.errorf), len(obs.tf),
+                                 vp(obs.tb), vp(obs.rvb), vp(obs.errorb), len(obs.tb), C.c_double(obs.Npoints),
+                                 int(var_in_norm), vp(theta), C.c_long(W), vp(logp), vp(grad), vp(hess), vp(status), cnt,
+                                 nthreads)
+    return logp, grad, hess, status, list(cnt)
+
+
+def mirror_loglik_d_dd(fixed, fp, fe, hill, obs, theta, dims=0):
+    fixed = np.ascontiguousarray(fixed, dtype=np.float64)
+    theta = np.ascontiguousarray(theta, dtype=np.float64)
+    fp = np.ascontiguousarray(fp, dtype=np.int32)
+    fe = np.ascontiguousarray(fe, dtype=np.int32)
+    W, nv = theta.shape[0], len(fp)
+    logp = np.zeros(W)
+    grad = np.zeros((W, nv))
+    hess = np.zeros((W, nv, nv))
+    status = np.zeros(W, dtype=np.int32)
+    cnt = (C.c_ulonglong * 2)()
+    rc = mirror().mirror_loglik_d_dd(fixed.shape[0], vp(fixed), nv, vp(fp), vp(fe), C.c_double(hill), dims,
+                                     vp(obs.tf), vp(obs.rvf), vp(obs.errorf), len(obs.tf),
+                                     vp(obs.tb), vp(obs.rvb), vp(obs.errorb), len(obs.tb), C.c_double(obs.Npoints),
+                                     vp(theta), C.c_longlong(W), vp(logp), vp(grad), vp(hess), vp(status), cnt)
+    assert rc == 0, rc
+    return logp, grad, hess, status, list(cnt)

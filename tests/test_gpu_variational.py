@@ -1,0 +1,131 @@
+"""GPU parity of the variational kernel (State.get_logp_d_dd, state.py:290-294) against the CPU oracle, through
+the C ABI.  Tolerances (BASELINE north_star): log-likelihood 1e-6 absolute, gradient and Hessian 1e-6 relative."""
+import numpy as np
+import pytest
+
+import rvtest as T
+
+pytestmark = pytest.mark.gpu
+Z2 = np.zeros((2, 7))
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from rvel_mcmc_b200 import _abi
+    c = _abi.Context(0)
+    yield c
+    c.close()
+
+
+def _handles(ctx, obs, fixed, fp, fe, hill):
+    from rvel_mcmc_b200 import _abi
+    oh = _abi.ObsHandle(ctx, obs.tf, obs.rvf, obs.errorf, obs.tb, obs.rvb, obs.errorb, obs.Npoints)
+    return oh, _abi.ModelHandle(ctx, fixed, fp, fe, hill)
+
+
+def _relerr(a, b):
+    return float((np.abs(a - b) / (np.abs(b) + 1e-6 * np.abs(b).max())).max())
+
+
+def test_kat_point_value_gradient_hessian(ctx):
+    obs = T.load_vels("HD155358.vels")
+    oh, m = _handles(ctx, obs, Z2, T.FP10, T.FE10, 2.0)
+    lg, gg, hg, sg = m.loglik_d_dd(oh, np.array([T.HD_SOL]))
+    lo, go, ho, so, _ = T.orc_logp_d_dd_batch(Z2, T.FP10, T.FE10, 2.0, obs, np.array([T.HD_SOL]))
+    assert sg[0] == 0
+    assert abs(lg[0] - T.KAT2_LOGP) < 5e-11
+    assert np.abs(gg / go - 1).max() < 1e-6
+    assert _relerr(hg, ho) < 1e-6
+    assert np.array_equal(hg[0], hg[0].T)
+
+
+def test_walker_ball_matches_oracle(ctx):
+    obs = T.load_vels("HD155358.vels")
+    oh, m = _handles(ctx, obs, Z2, T.FP10, T.FE10, 2.0)
+    theta = T.gaussian_ball(T.HD_SOL, T.HD_SCALE_VEC, 96, 11)
+    lg, gg, hg, sg = m.loglik_d_dd(oh, theta)
+    lo, go, ho, so, _ = T.orc_logp_d_dd_batch(Z2, T.FP10, T.FE10, 2.0, obs, theta)
+    assert np.array_equal(sg, so)
+    ok = so == 0
+    assert ok.sum() > 80
+    assert np.abs(lg[ok] - lo[ok]).max() < 1e-6
+    for w in np.where(ok)[0]:
+        assert np.abs(gg[w] - go[w]).max() <= 1e-6 * np.abs(go[w]).max(), w
+        assert np.abs(hg[w] - ho[w]).max() <= 1e-6 * np.abs(ho[w]).max(), w
+        assert _relerr(gg[w], go[w]) < 1e-5 and _relerr(hg[w], ho[w]) < 1e-5, w
+
+
+def test_status_prior_encounter_and_wide_ball(ctx):
+    obs = T.load_vels("HD155358.vels")
+    oh, m = _handles(ctx, obs, Z2, T.FP10, T.FE10, 2.0)
+    theta = T.gaussian_ball(T.HD_SOL, T.HD_SCALE_VEC, 64, 3, width=1.0)     # many encounters / prior violations
+    theta[0] = T.KAT5[1][0]
+    theta[1] = T.HD_SOL
+    theta[1][3] = 1e-6
+    lg, gg, hg, sg = m.loglik_d_dd(oh, theta)
+    lo, go, ho, so, _ = T.orc_logp_d_dd_batch(Z2, T.FP10, T.FE10, 2.0, obs, theta)
+    assert sg[0] == 3 and sg[1] == 1
+    assert (sg == so).mean() > 0.95          # borderline encounters may split on rounding
+    both = (sg == 0) & (so == 0)
+    assert np.abs(lg[both] - lo[both]).max() < 1e-6 * max(1.0, np.abs(lo[both]).max())
+    bad = sg != 0
+    assert np.isneginf(lg[bad]).all() and (gg[bad] == 0).all() and (hg[bad] == 0).all()
+
+
+@pytest.mark.parametrize("planets,free", [
+    ([{"a": 0.35, "m": 0.001965}], [("a",)]),
+    ([{"a": 0.2275, "h": 0.0, "k": 0.0, "m": 0.001965}], [("a", "h", "k")]),
+    ([{"m": 1e-3, "a": 0.3, "h": 0.02, "k": -0.03, "l": 0.4, "ix": 0.1, "iy": -0.05}], [("a", "ix", "m", "l", "iy")]),
+    ([{"m": 0.92e-3, "a": 0.2275, "h": -0.06, "k": 0.015, "l": -1.0, "ix": 0.05, "iy": 0.02},
+      {"m": 1.95e-3, "a": 0.3665, "h": 0.02, "k": 0.0, "l": 2.1, "ix": -0.03, "iy": 0.0}],
+     [("a", "ix", "h", "k", "m", "l", "iy"), ("a", "ix", "h", "k", "m", "l", "iy")]),
+    ([{"m": 0.92e-3, "a": 0.2275, "h": -0.06, "k": 0.015, "l": -1.0}, {"m": 1.95e-3, "a": 0.3665, "h": 0.02, "k": 0.0, "l": 2.1},
+      {"m": 1e-3, "a": 0.59, "h": 0.0, "k": 0.03, "l": 0.7}],
+     [("a", "h", "k", "m", "l"), ("a", "h", "k", "m", "l"), ("a", "h", "k", "m", "l")]),
+])
+def test_other_shapes(ctx, planets, free):
+    E = T.elems_from_planets(planets)
+    fp, fe, th = [], [], []
+    for i, keys in enumerate(free):
+        for k in keys:
+            fp.append(i); fe.append(T.ELEMS.index(k)); th.append(planets[i][k])
+    rng = np.random.RandomState(3)
+    obs = T.Obs()
+    obs.tf = np.concatenate([[0.0], np.sort(rng.uniform(0, 4.0, 12))])
+    obs.tb = np.sort(rng.uniform(-4.0, 0, 12))
+    obs.rvf = 1e-4 * rng.normal(size=13); obs.rvb = 1e-4 * rng.normal(size=12)
+    obs.errorf = np.full(13, 2e-4); obs.errorb = np.full(12, 2e-4)
+    obs.Npoints = 24
+    oh, m = _handles(ctx, obs, E, fp, fe, 1.0)
+    theta = np.array([th]) * (1 + 1e-4 * rng.normal(size=(4, len(th))))
+    lg, gg, hg, sg = m.loglik_d_dd(oh, theta)
+    lo, go, ho, so, _ = T.orc_logp_d_dd_batch(E, fp, fe, 1.0, obs, theta)
+    assert np.array_equal(sg, so) and (so == 0).all()
+    assert np.abs(lg - lo).max() < 1e-6 * max(1.0, np.abs(lo).max())
+    for w in range(4):
+        assert np.abs(gg[w] - go[w]).max() <= 1e-6 * np.abs(go[w]).max()
+        assert np.abs(hg[w] - ho[w]).max() <= 1e-6 * np.abs(ho[w]).max()
+
+
+def test_model_too_large_is_an_error(ctx):
+    from rvel_mcmc_b200 import _abi
+    planets = [{"m": 1e-3, "a": 0.3 + 0.2 * i, "h": 0.0, "k": 0.0, "l": 0.5 * i, "ix": 0.01, "iy": 0.0} for i in range(3)]
+    E = T.elems_from_planets(planets)
+    fp = [i for i in range(3) for _ in range(7)]
+    fe = list(range(7)) * 3
+    obs = T.load_vels("HD155358.vels")
+    oh, m = _handles(ctx, obs, E, fp, fe, 1.0)
+    with pytest.raises(_abi.RvGpuError):
+        m.loglik_d_dd(oh, np.array([E.reshape(-1)]))
+
+
+def test_state_api_get_logp_d_dd():
+    from rvel_mcmc_b200 import observations, state
+    import os
+    obs = observations.Observation_FromFile(os.path.join(T.GOLDEN, "HD155358.vels"), Npoints=100)
+    s = state.State(T.planets_from_vec(T.HD_SOL))
+    s.hillRadiusFactor = 2.
+    logp, d, dd = s.get_logp_d_dd(obs)
+    lo, go, ho, so, _ = T.orc_logp_d_dd_batch(Z2, T.FP10, T.FE10, 2.0, T.load_vels("HD155358.vels"), np.array([T.HD_SOL]))
+    assert abs(logp - lo[0]) < 1e-9 and np.abs(d / go[0] - 1).max() < 1e-6 and _relerr(dd, ho[0]) < 1e-6
+    assert s.logp == logp and s.logp_d is d and s.logp_dd is dd      # cached (state.py:291-294)
