@@ -128,6 +128,17 @@ int rv_mh_steps_dev(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, doubl
                     const double* d_scales, double step_size, uint64_t seed, uint64_t first_chain_id,
                     uint32_t first_step, int nsteps, int64_t W, uint64_t* d_n_accept, void* stream);
 
+/* ---- Smala.step (mcmc.py:167-187) for W independent chains, nsteps steps, device-resident ---------------------- */
+/* theta[W][nvars]: start state in, final state out; logp[W] out.  Per step and chain: SoftAbs metric of the Hessian
+ * (mcmc.py:135-139, alpha), proposal theta* = mu + eps*chol(Ginv) z (mcmc.py:144-153), one value+gradient+Hessian
+ * evaluation at theta*, accept iff exp(logp* - logp + q(theta|theta*) - q(theta*|theta)) > u.  A proposal outside the hard
+ * prior or raising Encounter is rejected (mcmc.py:171,176).  Where the reference quits on LinAlgError (mcmc.py:179-183)
+ * the step is rejected and status[w] is set to RV_NOT_SPD (status[w] is otherwise the status of the start state).
+ * RNG and optional outputs as rv_mh_run.                                                                              */
+int rv_smala_run(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, double* theta, double* logp, double eps,
+                 double alpha, uint64_t seed, uint64_t first_chain_id, uint32_t first_step, int nsteps, int thin, int64_t W,
+                 double* chain, double* chain_logp, uint64_t* n_accept, uint8_t* accepted, int32_t* status);
+
 /* ---- work accounting: force evaluations and IAS15 step attempts since the last reset ----------- */
 int rv_work_counters(rv_ctx* ctx, uint64_t out[2], int reset);
 int rv_count_work(rv_ctx* ctx, int enable);     /* off by default (atomics per item when on)       */

@@ -55,6 +55,9 @@ _SIGNATURES = {
     "rv_mh_run": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_double,
                             C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p,
                             C.c_void_p, C.c_void_p]),
+    "rv_smala_run": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double,
+                               C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p,
+                               C.c_void_p, C.c_void_p, C.c_void_p]),
     "rv_stretch_run": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double,
                                  C.c_uint64, C.c_uint32, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_void_p]),
@@ -268,6 +271,25 @@ class ModelHandle(object):
                                               int(first_step), int(nsteps), int(thin), W, _ptr(chain), _ptr(chain_lp),
                                               _ptr(nacc), _ptr(acc)), "rv_mh_run")
         return dict(theta=theta, logp=lp, chain=chain, chain_logp=chain_lp, n_accept=nacc, accepted=acc)
+
+    def smala_run(self, obs, theta, eps, alpha, nsteps, seed=0, first_chain_id=0, first_step=0, thin=1,
+                  record_chain=True, record_accepts=False):
+        """W independent SMALA chains (Smala.step, mcmc.py:167-187) run on the device.
+        Returns dict(theta, logp, chain, chain_logp, n_accept[W], accepted[nsteps][W], status[W])."""
+        theta = self._theta(theta).copy()
+        W = theta.shape[0]
+        lp = np.zeros(W)
+        rows = nsteps // thin
+        chain = np.zeros((rows, W, self.nvars)) if record_chain else None
+        chain_lp = np.zeros((rows, W)) if record_chain else None
+        nacc = np.zeros(W, dtype=np.uint64)
+        acc = np.zeros((nsteps, W), dtype=np.uint8) if record_accepts else None
+        status = np.zeros(W, dtype=np.int32)
+        self.ctx.check(self.ctx.lib.rv_smala_run(self.ctx.h, self.h, obs.h, _ptr(theta), _ptr(lp), float(eps), float(alpha),
+                                                 int(seed), int(first_chain_id), int(first_step), int(nsteps), int(thin), W,
+                                                 _ptr(chain), _ptr(chain_lp), _ptr(nacc), _ptr(acc), _ptr(status)),
+                       "rv_smala_run")
+        return dict(theta=theta, logp=lp, chain=chain, chain_logp=chain_lp, n_accept=nacc, accepted=acc, status=status)
 
     def stretch_run(self, obs, theta, nsteps, a=2.0, seed=0, first_step=0, thin=1, lnp=None, record_chain=True,
                     record_accepts=False):

@@ -37,6 +37,12 @@ struct rv_ctx {
     double* d_vpart; size_t cap_vpart;
     double* d_grad; size_t cap_grad;
     double* d_hess; size_t cap_hess;
+    double* d_pgrad; size_t cap_pgrad;
+    double* d_phess; size_t cap_phess;
+    double* d_qf; size_t cap_qf;
+    double* d_lascr; size_t cap_lascr;
+    int* d_geo; size_t cap_geo;
+    int* d_flag; size_t cap_flag;
     char err[512];
 };
 struct rv_obs {
@@ -127,6 +133,7 @@ int rv_ctx_destroy(rv_ctx* c) {
     cudaFree(c->d_prop); cudaFree(c->d_plogp); cudaFree(c->d_pstatus); cudaFree(c->d_zz); cudaFree(c->d_scales);
     cudaFree(c->d_chain); cudaFree(c->d_chainlp); cudaFree(c->d_nacc); cudaFree(c->d_acc);
     cudaFree(c->d_vpart); cudaFree(c->d_grad); cudaFree(c->d_hess);
+    cudaFree(c->d_pgrad); cudaFree(c->d_phess); cudaFree(c->d_qf); cudaFree(c->d_lascr); cudaFree(c->d_geo); cudaFree(c->d_flag);
     cudaStreamDestroy(c->stream);
     delete c;
     return 0;
@@ -516,6 +523,70 @@ int rv_stretch_run(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, double
     }
     if (n_accept) CU(ctx, cudaMemcpyAsync(n_accept, ctx->d_nacc, (size_t)W * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
     if (accepted) CU(ctx, cudaMemcpyAsync(accepted, ctx->d_acc, (size_t)nsteps * W, cudaMemcpyDeviceToHost, s));
+    CU(ctx, cudaStreamSynchronize(s));
+    return 0;
+}
+
+int rv_smala_run(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, double* theta, double* logp, double eps,
+                 double alpha, uint64_t seed, uint64_t first_chain_id, uint32_t first_step, int nsteps, int thin, int64_t W,
+                 double* chain, double* chain_logp, uint64_t* n_accept, uint8_t* accepted, int32_t* status) {
+    if (!ctx || !model || !obs || !theta || !logp) return fail(ctx, -1, "rv_smala_run: NULL argument");
+    if (W <= 0 || nsteps < 0) return fail(ctx, -2, "rv_smala_run: bad size");
+    const int nv = model->h.nvars;
+    if (nv < 1) return fail(ctx, -2, "rv_smala_run: the model has no free parameter");
+    if (thin < 1) thin = 1;
+    CU(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const size_t nvs = (size_t)nv;
+    const long long rows = chain ? nsteps / thin : 0;
+    if (int rc = ensure(ctx, &ctx->d_theta, &ctx->cap_theta, (size_t)W * nvs)) return rc;
+    if (int rc = ensure(ctx, &ctx->d_logp, &ctx->cap_logp, (size_t)W)) return rc;
+    if (int rc = ensure(ctx, &ctx->d_status, &ctx->cap_status, (size_t)W)) return rc;
+    if (int rc = ensure(ctx, &ctx->d_grad, &ctx->cap_grad, (size_t)W * nvs)) return rc;
+    if (int rc = ensure(ctx, &ctx->d_hess, &ctx->cap_hess, (size_t)W * nvs * nvs)) return rc;
+    if (int rc = ensure(ctx, &ctx->d_prop, &ctx->cap_prop, (size_t)W * nvs)) return rc;
+    if (int rc = ensure(ctx, &ctx->d_plogp, &ctx->cap_plogp, (size_t)W)) return rc;
+    if (int rc = ensure(ctx, &ctx->d_pstatus, &ctx->cap_pstatus, (size_t)W)) return rc;
+    if (int rc = ensure(ctx, &ctx->d_pgrad, &ctx->cap_pgrad, (size_t)W * nvs)) return rc;
+    if (int rc = ensure(ctx, &ctx->d_phess, &ctx->cap_phess, (size_t)W * nvs * nvs)) return rc;
+    if (int rc = ensure(ctx, &ctx->d_qf, &ctx->cap_qf, (size_t)W)) return rc;
+    if (int rc = ensure(ctx, &ctx->d_lascr, &ctx->cap_lascr, (size_t)W * 5 * nvs * nvs)) return rc;
+    if (int rc = ensure(ctx, &ctx->d_geo, &ctx->cap_geo, (size_t)W)) return rc;
+    if (int rc = ensure(ctx, &ctx->d_flag, &ctx->cap_flag, (size_t)W)) return rc;
+    if (int rc = ensure(ctx, &ctx->d_nacc, &ctx->cap_nacc, (size_t)W)) return rc;
+    if (rows) {
+        if (int rc = ensure(ctx, &ctx->d_chain, &ctx->cap_chain, (size_t)rows * W * nvs)) return rc;
+        if (int rc = ensure(ctx, &ctx->d_chainlp, &ctx->cap_chainlp, (size_t)rows * W)) return rc;
+    }
+    if (accepted) if (int rc = ensure(ctx, &ctx->d_acc, &ctx->cap_acc, (size_t)nsteps * W + 1)) return rc;
+    CU(ctx, cudaMemcpyAsync(ctx->d_theta, theta, (size_t)W * nv * sizeof(double), cudaMemcpyHostToDevice, s));
+    CU(ctx, cudaMemsetAsync(ctx->d_nacc, 0, (size_t)W * sizeof(unsigned long long), s));
+    // state.get_logp_d_dd at the start state (mcmc.py:145)
+    if (int rc = var_dev_impl(ctx, model, obs, ctx->d_theta, W, ctx->d_logp, ctx->d_grad, ctx->d_hess, ctx->d_status, s)) return rc;
+    CU(ctx, cudaMemcpyAsync(ctx->d_flag, ctx->d_status, (size_t)W * sizeof(int), cudaMemcpyDeviceToDevice, s));
+    long long row = 0;
+    for (int k = 0; k < nsteps; k++) {
+        const unsigned step = first_step + (unsigned)k;
+        CU(ctx, rv::launch_smala_propose(ctx->d_theta, ctx->d_grad, ctx->d_hess, ctx->d_status, nv, W, eps, alpha, seed,
+                                         first_chain_id, step, ctx->d_prop, ctx->d_qf, ctx->d_geo, ctx->d_lascr, s));
+        if (int rc = var_dev_impl(ctx, model, obs, ctx->d_prop, W, ctx->d_plogp, ctx->d_pgrad, ctx->d_phess, ctx->d_pstatus, s)) return rc;
+        const bool rec = rows && ((k + 1) % thin == 0);
+        CU(ctx, rv::launch_smala_accept(ctx->d_theta, ctx->d_logp, ctx->d_grad, ctx->d_hess, ctx->d_prop, ctx->d_plogp,
+                                        ctx->d_pgrad, ctx->d_phess, ctx->d_pstatus, ctx->d_geo, ctx->d_qf, nv, W, eps, alpha,
+                                        seed, first_chain_id, step, ctx->d_nacc, accepted ? ctx->d_acc + (size_t)k * W : nullptr,
+                                        ctx->d_flag, rec ? ctx->d_chain + (size_t)row * W * nv : nullptr,
+                                        rec ? ctx->d_chainlp + (size_t)row * W : nullptr, ctx->d_lascr, s));
+        if (rec) row++;
+    }
+    CU(ctx, cudaMemcpyAsync(theta, ctx->d_theta, (size_t)W * nv * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CU(ctx, cudaMemcpyAsync(logp, ctx->d_logp, (size_t)W * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (rows) {
+        CU(ctx, cudaMemcpyAsync(chain, ctx->d_chain, (size_t)rows * W * nv * sizeof(double), cudaMemcpyDeviceToHost, s));
+        if (chain_logp) CU(ctx, cudaMemcpyAsync(chain_logp, ctx->d_chainlp, (size_t)rows * W * sizeof(double), cudaMemcpyDeviceToHost, s));
+    }
+    if (n_accept) CU(ctx, cudaMemcpyAsync(n_accept, ctx->d_nacc, (size_t)W * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    if (accepted) CU(ctx, cudaMemcpyAsync(accepted, ctx->d_acc, (size_t)nsteps * W, cudaMemcpyDeviceToHost, s));
+    if (status) CU(ctx, cudaMemcpyAsync(status, ctx->d_flag, (size_t)W * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     CU(ctx, cudaStreamSynchronize(s));
     return 0;
 }

@@ -29,5 +29,14 @@ cudaError_t launch_stretch_accept(double* S, double* lnp, const double* q, const
                                   const double* zz, int nvars, long long nS, unsigned long long seed,
                                   unsigned long long id0_S, unsigned step, unsigned half, unsigned long long* n_accept,
                                   unsigned char* accepted, cudaStream_t s);
+cudaError_t launch_smala_propose(const double* theta, const double* grad, const double* hess, const int* cur_status, int n,
+                                 long long W, double eps, double alpha, unsigned long long seed, unsigned long long first_id,
+                                 unsigned step, double* prop, double* q_fwd, int* geo_status, double* scratch, cudaStream_t s);
+cudaError_t launch_smala_accept(double* theta, double* logp, double* grad, double* hess, const double* prop,
+                                const double* p_logp, const double* p_grad, const double* p_hess, const int* p_status,
+                                const int* geo_status, const double* q_fwd, int n, long long W, double eps, double alpha,
+                                unsigned long long seed, unsigned long long first_id, unsigned step,
+                                unsigned long long* n_accept, unsigned char* accepted, int* flag, double* chain_row,
+                                double* chain_logp_row, double* scratch, cudaStream_t s);
 cudaError_t launch_mask_logp(double* logp, const int* status, long long W, cudaStream_t s);
 }  // namespace rv

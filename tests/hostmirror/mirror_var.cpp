@@ -85,3 +85,25 @@ extern "C" int mirror_loglik_d_dd(int P, const double* fixed, int nvars, const i
     if (counters) { counters[0] = work[0]; counters[1] = work[1]; }
     return 0;
 }
+
+// ---- per-chain SMALA arithmetic (rv_smala.cuh) ------------------------------------------------------------
+#include "../../rvel_mcmc_b200/csrc/rv_smala.cuh"
+
+extern "C" int mirror_smala_propose(int n, const double* th, const double* g, const double* H, int cur_status, double eps,
+                                    double alpha, unsigned long long seed, unsigned long long id, unsigned step,
+                                    double* prop, double* q_fwd) {
+    std::vector<double> scr((size_t)5 * n * n, 0.0);
+    double q = 0.0;
+    const int r = rv::smala_propose_one(n, th, g, H, cur_status, eps, alpha, seed, id, step, prop, q, scr.data());
+    *q_fwd = q;
+    return r;
+}
+
+extern "C" int mirror_smala_accept(int n, const double* th, double logp, const double* prop, double p_logp,
+                                   const double* p_grad, const double* p_hess, int p_status, int geo_status, double q_fwd,
+                                   double eps, double alpha, unsigned long long seed, unsigned long long id, unsigned step,
+                                   int* flag) {
+    std::vector<double> scr((size_t)5 * n * n, 0.0);
+    return rv::smala_accept_one(n, th, logp, prop, p_logp, p_grad, p_hess, p_status, geo_status, q_fwd, eps, alpha, seed, id,
+                                step, flag, scr.data());
+}
