@@ -37,7 +37,7 @@ class ShardedStretch(object):
             self.fn(S, lo, Cfull, lnp_local[half * self.n_loc:(half + 1) * self.n_loc], step, half)
             if self.world > 1:
                 full_half = theta[half * self.h:(half + 1) * self.h]
-                self.dist.all_gather_into_tensor(full_half, S)
+                self.dist.all_gather_into_tensor(full_half, S.clone())
 
     def gather_lnp(self, lnp_local, torch):
         """Full lnp[W] on every rank, in ensemble order."""
@@ -89,3 +89,57 @@ def ess(chain):
         taus.append(np.nanmean(t))
     tau = float(np.nanmax(taus))
     return n * w / max(tau, 1.0), tau
+
+
+def stretch_run_sharded(model, obs_handle, theta0, nsteps, a=2.0, seed=0, thin=1, device=None, dist=None,
+                        record_chain=True):
+    """Affine stretch ensemble of W walkers sharded over the ranks of `dist` (torch.distributed, NCCL on GPUs).
+
+    Every rank holds the full position array in HBM, owns W/(2*world) walkers of each half, moves them with
+    rv_stretch_half_dev and all-gathers the updated half (the only exchange).  With world == 1 (or
+    dist None) this is the single-GPU ensemble.  Returns dict(theta[W][nvars], lnp[W], chain, chain_lnp, n_accept[W])
+    as numpy arrays, identical on every rank and -- because the random numbers are keyed by the ensemble index --
+    identical for every world size.
+    """
+    import torch
+    world = dist.get_world_size() if dist is not None else 1
+    rank = dist.get_rank() if dist is not None else 0
+    theta0 = np.ascontiguousarray(theta0, dtype=np.float64)
+    W, nv = theta0.shape
+    dev = device if device is not None else torch.device("cuda", model.ctx.device)
+    theta = torch.from_numpy(theta0).to(dev)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+
+    def half_fn(S, id0, Cfull, lnp_view, step, half):
+        model.stretch_half_dev(obs_handle, S.data_ptr(), S.shape[0], id0, Cfull.data_ptr(), Cfull.shape[0],
+                               lnp_view.data_ptr(), a, seed, step, half, d_n_accept=nacc_view[half].data_ptr(),
+                               stream=stream)
+
+    sh = ShardedStretch(half_fn, W, nv, rank, world, dist)
+    n_loc = sh.n_loc
+    # lnprob0 of the owned walkers (emcee evaluates the whole ensemble on the first call, mcmc.py:57-59)
+    lnp_local = torch.empty(2 * n_loc, dtype=torch.float64, device=dev)
+    st_local = torch.empty(2 * n_loc, dtype=torch.int32, device=dev)
+    nacc = torch.zeros(2 * n_loc, dtype=torch.int64, device=dev)
+    nacc_view = [nacc[:n_loc], nacc[n_loc:]]
+    for half in (0, 1):
+        lo, hi = sh.owned(half)
+        model.loglik_dev(obs_handle, theta[lo:hi].data_ptr(), n_loc, lnp_local[half * n_loc:].data_ptr(),
+                         st_local[half * n_loc:].data_ptr(), stream)
+    lnp_local[st_local != 0] = float("-inf")
+    rows = nsteps // thin if record_chain else 0
+    chain = torch.empty((rows, W, nv), dtype=torch.float64, device=dev) if rows else None
+    chain_lnp = torch.empty((rows, W), dtype=torch.float64, device=dev) if rows else None
+    row = 0
+    for k in range(nsteps):
+        sh.step(theta, lnp_local, k)
+        if rows and (k + 1) % thin == 0:
+            chain[row] = theta
+            chain_lnp[row] = sh.gather_lnp(lnp_local, torch)
+            row += 1
+    lnp = sh.gather_lnp(lnp_local, torch)
+    nacc_full = sh.gather_lnp(nacc.to(torch.float64), torch)
+    torch.cuda.synchronize(dev)
+    return dict(theta=theta.cpu().numpy(), lnp=lnp.cpu().numpy(),
+                chain=chain.cpu().numpy() if rows else None, chain_lnp=chain_lnp.cpu().numpy() if rows else None,
+                n_accept=nacc_full.cpu().numpy().astype(np.uint64))

@@ -142,3 +142,19 @@ def test_reference_api_samplers_run_on_gpu():
     assert bundle.mcmc_chain.shape == (256, 3) and bundle.mcmc_is_emcee
     act = driver.ac_times(bundle)
     assert act.shape == (3,)
+
+
+def test_two_gpu_sharded_samplers_equal_single_gpu():
+    """N=2 NCCL path (skipped on a 1-GPU box): sharded stretch ensemble and MH shards equal the single-GPU runs."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533",
+                        os.path.join(T.ROOT, "bench_scripts", "multigpu_check.py"), "--walkers", "512", "--steps", "4"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert '"stretch_equal_single_gpu": true' in r.stdout and '"mh_shard_equal_single_gpu": true' in r.stdout
