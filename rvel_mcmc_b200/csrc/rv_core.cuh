@@ -222,8 +222,8 @@ RV_D void warp_converge() {
 #endif
 }
 
-// History store for the rejected-step re-prediction (rebound's br/er): 2*7*NC doubles per lane,
-// strided so that consecutive lanes touch consecutive doubles (shared memory on the device).
+// Per-lane store of the coefficients touched once per step: rebound's er, br (rejected-step re-prediction) and e:
+// 3*7*NC doubles, strided so that consecutive lanes touch consecutive doubles (shared memory on the device).
 struct Hist {
     double* p;
     int stride;
@@ -231,8 +231,17 @@ struct Hist {
 };
 
 // ---------------------------------------------------------------------------------------------
-// One walker (or one planet of a walker when PL == 1).
-template <int P, int D, int PL>
+// One walker (or one planet of a walker when PL == 1): state, gravity, encounter test, set-up.  The IAS15 step
+// itself is WalkerG::attempt (rv_core_g.cuh).
+// VAR: compile-time tuning switch -- bit1: IAS15 tables read from the constant bank (else folded into immediates;
+// measured faster on B200, profiles/r01c_variants.txt).
+template <int VAR> RV_D double tH(int n) { if constexpr ((VAR & 2) != 0) return rvtabm::H[n]; else return rvtab::H[n]; }
+template <int VAR> RV_D double tGA(int n) { if constexpr ((VAR & 2) != 0) return rvtabm::GA[n]; else return rvtab::GA[n]; }
+template <int VAR> RV_D double tPRED(int n, int k) { if constexpr ((VAR & 2) != 0) return rvtabm::PRED[n][k]; else return rvtab::PRED[n][k]; }
+template <int VAR> RV_D double tGB(int n, int k) { if constexpr ((VAR & 2) != 0) return rvtabm::GB[n][k]; else return rvtab::GB[n][k]; }
+template <int VAR> RV_D double tCC(int n, int k) { if constexpr ((VAR & 2) != 0) return rvtabm::CC[n][k]; else return rvtab::CC[n][k]; }
+template <int VAR> RV_D double tDD(int n, int k) { if constexpr ((VAR & 2) != 0) return rvtabm::DD[n][k]; else return rvtab::DD[n][k]; }
+template <int P, int D, int PL, int VAR = 0>
 struct Walker {
     static constexpr int G = P / PL;    // lanes per walker
     static constexpr int NC = PL * D;   // coordinates held by this lane
@@ -242,7 +251,7 @@ struct Walker {
     Hist hist;
     // IAS15 state
     double x0[NC], v0[NC], a0[NC], ha0[NC], csx[NC], csv[NC];
-    double b[7][NC], g[7][NC], e[7][NC];
+    double b[7][NC];      // b between step attempts; the g coefficients inside the predictor-corrector loop
     double t, dt, dt_last_done;
     // masses: own planets and (PL==1) the other planets in relative rank order
     double gm[PL];        // G*m of own planets
@@ -391,228 +400,6 @@ struct Walker {
     // barycentric x-velocity of the star = the RV observable (state.py:72)
     RV_D double star_vx() const { return star_of<false>(v0, 0); }
 
-    // ---- one Gauss-Radau substep: predict positions at h_n, force, update g_{n-1} and b ------------
-    // `commit` = this lane's walker is still iterating; otherwise its b,g stay frozen while the warp
-    // finishes the pass for the other walkers.
-    template <int n>
-    RV_D void substep(bool commit, double (&xp)[NC], double (&at)[NC], double (&dg6)[NC]) {
-        const double dth = dt * rvtab::H[n];
-        double xn[NC], an[NC];
-#pragma unroll
-        for (int c = 0; c < NC; c++) {
-            double p0 = fma(rvtab::PRED[n][0], b[0][c], ha0[c]);
-            p0 = fma(rvtab::PRED[n][1], b[1][c], p0);
-            p0 = fma(rvtab::PRED[n][2], b[2][c], p0);
-            double p1 = rvtab::PRED[n][3] * b[3][c];
-            p1 = fma(rvtab::PRED[n][4], b[4][c], p1);
-            p1 = fma(rvtab::PRED[n][5], b[5][c], p1);
-            p1 = fma(rvtab::PRED[n][6], b[6][c], p1);
-            const double inner = fma(dth, p0 + p1, v0[c]);
-            xn[c] = x0[c] + fma(dth, inner, -csx[c]);
-        }
-        accel(xn, an);
-#pragma unroll
-        for (int c = 0; c < NC; c++) {
-            const double gk = an[c] - a0[c];
-            double s0 = gk * rvtab::GA[n], s1 = 0.0;
-#pragma unroll
-            for (int i = 0; i < n - 1; i++) {
-                if (i & 1) s1 = fma(-g[i][c], rvtab::GB[n][i], s1);
-                else s0 = fma(-g[i][c], rvtab::GB[n][i], s0);
-            }
-            const double gn = s0 + s1;
-            const double tmp = sel(commit, gn - g[n - 1][c], 0.0);
-            g[n - 1][c] = sel(commit, gn, g[n - 1][c]);
-#pragma unroll
-            for (int i = 0; i < n - 1; i++) b[i][c] = fma(tmp, rvtab::CC[n - 1][i], b[i][c]);
-            b[n - 1][c] += tmp;
-            if (n == 7) {
-                dg6[c] = sel(commit, tmp, dg6[c]);
-                at[c] = sel(commit, an[c], at[c]);
-                xp[c] = sel(commit, xn[c], xp[c]);
-            }
-        }
-    }
-
-    // predict_next_step (rebound): new e,b from (_e,_b) scaled by q = dt_new/dt_old.
-    RV_D void predict(double q, const double (&_e)[7], const double (&_b)[7], int c) {
-        if (q > 20.0) {
-#pragma unroll
-            for (int k = 0; k < 7; k++) { e[k][c] = 0.0; b[k][c] = 0.0; }
-            return;
-        }
-        const double q1 = q, q2 = q1 * q1, q3 = q1 * q2, q4 = q2 * q2, q5 = q2 * q3, q6 = q3 * q3, q7 = q3 * q4;
-        double be[7];
-#pragma unroll
-        for (int k = 0; k < 7; k++) be[k] = _b[k] - _e[k];
-        e[0][c] = q1 * (_b[6] * 7.0 + _b[5] * 6.0 + _b[4] * 5.0 + _b[3] * 4.0 + _b[2] * 3.0 + _b[1] * 2.0 + _b[0]);
-        e[1][c] = q2 * (_b[6] * 21.0 + _b[5] * 15.0 + _b[4] * 10.0 + _b[3] * 6.0 + _b[2] * 3.0 + _b[1]);
-        e[2][c] = q3 * (_b[6] * 35.0 + _b[5] * 20.0 + _b[4] * 10.0 + _b[3] * 4.0 + _b[2]);
-        e[3][c] = q4 * (_b[6] * 35.0 + _b[5] * 15.0 + _b[4] * 5.0 + _b[3]);
-        e[4][c] = q5 * (_b[6] * 21.0 + _b[5] * 6.0 + _b[4]);
-        e[5][c] = q6 * (_b[6] * 7.0 + _b[5]);
-        e[6][c] = q7 * _b[6];
-#pragma unroll
-        for (int k = 0; k < 7; k++) b[k][c] = e[k][c] + be[k];
-    }
-
-    // ---- one IAS15 step attempt (rebound: reb_integrator_ias15_step) ------------------------------
-    // Executed by ALL lanes of the warp together (full-mask shuffles inside); lanes whose walker is not
-    // mid-integration pass active=false and leave their state untouched.
-    // Returns: bit0 = step accepted, bit1 = an encounter is flagged at the post-step positions.
-    RV_D int attempt(bool active) {
-        warp_converge();
-        if (active) { n_attempt++; }
-        accel(x0, a0);   // rebound evaluates the force once per step; a retry re-derives the same a0
-#pragma unroll
-        for (int c = 0; c < NC; c++) {
-            ha0[c] = 0.5 * a0[c];
-#pragma unroll
-            for (int j = 0; j < 7; j++) {
-                double s = 0.0;
-#pragma unroll
-                for (int k = 6; k > j; k--) s = fma(b[k][c], rvtab::DD[k][j], s);
-                g[j][c] = s + b[j][c];
-            }
-        }
-        double xp[NC], at[NC], dg6[NC];
-#pragma unroll
-        for (int c = 0; c < NC; c++) { xp[c] = x0[c]; at[c] = a0[c]; dg6[c] = 0.0; }
-        double pc_err = 1e300, pc_last = 2.0;
-        int it = 0;
-        bool iterating = active;
-        while (true) {
-            if (iterating && (pc_err < 1e-16 || (it > 2 && pc_last <= pc_err) || it >= 12)) iterating = false;
-            if (!warp_any(iterating)) break;
-            if (iterating) { pc_last = pc_err; it++; }
-            substep<1>(iterating, xp, at, dg6);
-            substep<2>(iterating, xp, at, dg6);
-            substep<3>(iterating, xp, at, dg6);
-            substep<4>(iterating, xp, at, dg6);
-            substep<5>(iterating, xp, at, dg6);
-            substep<6>(iterating, xp, at, dg6);
-            substep<7>(iterating, xp, at, dg6);
-            // convergence monitor: max |change of b6| / max |a| over all coordinates (epsilon_global)
-            double maxdg = 0.0, maxat = 0.0;
-#pragma unroll
-            for (int c = 0; c < NC; c++) {
-                const double ak = fabs(at[c]), dg = fabs(dg6[c]);
-                if (is_normal(ak) && ak > maxat) maxat = ak;
-                if (is_normal(dg) && dg > maxdg) maxdg = dg;
-            }
-            if (warp_any(star_in_norm)) {
-#pragma unroll
-                for (int d = 0; d < D; d++) {
-                    const double sa = fabs(star_of<true>(at, d)), sg = fabs(star_of<true>(dg6, d));
-                    if (star_in_norm && is_normal(sa) && sa > maxat) maxat = sa;
-                    if (star_in_norm && is_normal(sg) && sg > maxdg) maxdg = sg;
-                }
-            }
-            maxdg = grp.template gmax<true>(maxdg);
-            maxat = grp.template gmax<true>(maxat);
-            if (iterating) { pc_err = maxdg / maxat; n_force += 7; }
-        }
-        if (active) n_force += 1;
-        // step-size control (all lanes compute; only active ones use it)
-        double maxak = 0.0, maxb6 = 0.0;
-#pragma unroll
-        for (int pl = 0; pl < PL; pl++) {
-            double v2 = 0.0, x2 = 0.0;
-#pragma unroll
-            for (int d = 0; d < D; d++) { v2 = fma(v0[pl * D + d], v0[pl * D + d], v2); x2 = fma(xp[pl * D + d], xp[pl * D + d], x2); }
-            const bool keep = !(fabs(v2 * dt * dt / x2) < 1e-16);
-#pragma unroll
-            for (int d = 0; d < D; d++) {
-                const double ak = fabs(at[pl * D + d]), b6 = fabs(b[6][pl * D + d]);
-                if (keep && is_normal(ak) && ak > maxak) maxak = ak;
-                if (keep && is_normal(b6) && b6 > maxb6) maxb6 = b6;
-            }
-        }
-        if (warp_any(star_in_norm)) {
-            double v2 = 0.0, x2 = 0.0, sa[D], sb[D];
-#pragma unroll
-            for (int d = 0; d < D; d++) {
-                const double sv = star_of<true>(v0, d), sx = star_of<true>(xp, d);
-                v2 = fma(sv, sv, v2); x2 = fma(sx, sx, x2);
-                sa[d] = fabs(star_of<true>(at, d)); sb[d] = fabs(star_of<true>(b[6], d));
-            }
-            const bool keep = star_in_norm && !(fabs(v2 * dt * dt / x2) < 1e-16);
-#pragma unroll
-            for (int d = 0; d < D; d++) {
-                if (keep && is_normal(sa[d]) && sa[d] > maxak) maxak = sa[d];
-                if (keep && is_normal(sb[d]) && sb[d] > maxb6) maxb6 = sb[d];
-            }
-        }
-        maxak = grp.template gmax<true>(maxak);
-        maxb6 = grp.template gmax<true>(maxb6);
-        int result = 0;
-        if (active) {
-            const double err = maxb6 / maxak;
-            const double dt_done = dt;
-            double dt_new;
-            if (is_normal(err)) dt_new = pow(epsilon / err, 1.0 / 7.0) * dt_done;
-            else dt_new = dt_done / 0.25;
-            if (fabs(dt_new / dt_done) < 0.25) {
-                // rejected: (x0,v0,a0) untouched; re-predict b,e from the last accepted step's copies
-                dt = dt_new;
-                if (dt_last_done != 0.0) {
-                    const double q = dt / dt_last_done;
-#pragma unroll
-                    for (int c = 0; c < NC; c++) {
-                        double _e[7], _b[7];
-#pragma unroll
-                        for (int k = 0; k < 7; k++) { _e[k] = hist.at(k * NC + c); _b[k] = hist.at((7 + k) * NC + c); }
-                        predict(q, _e, _b, c);
-                    }
-                }
-            } else {
-                if (fabs(dt_new / dt_done) > 1.0 && dt_new / dt_done > 4.0) dt_new = dt_done / 0.25;
-                dt = dt_new;
-                const double dt2 = dt_done * dt_done;
-#pragma unroll
-                for (int c = 0; c < NC; c++) {
-                    {
-                        const double a = x0[c];
-                        double s = b[6][c] * (1. / 72.);
-                        s = fma(b[5][c], 1. / 56., s); s = fma(b[4][c], 1. / 42., s); s = fma(b[3][c], 1. / 30., s);
-                        s = fma(b[2][c], 1. / 20., s); s = fma(b[1][c], 1. / 12., s); s = fma(b[0][c], 1. / 6., s);
-                        s = fma(a0[c], 0.5, s);
-                        csx[c] += fma(s, dt2, v0[c] * dt_done);
-                        x0[c] = a + csx[c];
-                        csx[c] += a - x0[c];
-                    }
-                    {
-                        const double a = v0[c];
-                        double s = b[6][c] * (1. / 8.);
-                        s = fma(b[5][c], 1. / 7., s); s = fma(b[4][c], 1. / 6., s); s = fma(b[3][c], 1. / 5., s);
-                        s = fma(b[2][c], 1. / 4., s); s = fma(b[1][c], 1. / 3., s); s = fma(b[0][c], 1. / 2., s);
-                        s += a0[c];
-                        csv[c] = fma(s, dt_done, csv[c]);
-                        v0[c] = a + csv[c];
-                        csv[c] += a - v0[c];
-                    }
-                }
-                t += dt_done;
-                dt_last_done = dt_done;
-                const double q = dt / dt_done;
-#pragma unroll
-                for (int c = 0; c < NC; c++) {
-                    double _e[7], _b[7];
-#pragma unroll
-                    for (int k = 0; k < 7; k++) {
-                        _e[k] = e[k][c]; _b[k] = b[k][c];
-                        hist.at(k * NC + c) = _e[k]; hist.at((7 + k) * NC + c) = _b[k];
-                    }
-                    predict(q, _e, _b, c);
-                }
-                result = 1;
-            }
-        }
-        warp_converge();
-        if (encounter<true>()) result |= 2;
-        return result;
-    }
-
     // ---- item setup: theta -> elements -> barycentric cartesian (setup_sim) ---------------------
     // returns status (ST_OK or ST_PRIOR).  check_prior=false mirrors get_rv (no prior test, state.py:61).
     RV_D int setup(const Model* __restrict__ md, const double* __restrict__ theta, bool check_prior) {
@@ -681,8 +468,8 @@ struct Walker {
             csx[c] = 0.0; csv[c] = 0.0; a0[c] = 0.0; ha0[c] = 0.0;
 #pragma unroll
             for (int k = 0; k < 7; k++) {
-                b[k][c] = 0.0; e[k][c] = 0.0; g[k][c] = 0.0;
-                hist.at(k * NC + c) = 0.0; hist.at((7 + k) * NC + c) = 0.0;
+                b[k][c] = 0.0;
+                hist.at(k * NC + c) = 0.0; hist.at((7 + k) * NC + c) = 0.0; hist.at((14 + k) * NC + c) = 0.0;
             }
         }
         t = 0.0; dt = md->dt0; dt_last_done = 0.0;

@@ -1,0 +1,254 @@
+// rv_core_g.cuh -- IAS15 step with the predictor-corrector loop written on the g coefficients only.
+//
+// rebound keeps both g and b current inside the loop (b += dg * c after every substep) because its predictor reads b.
+// Here the predictor reads g through PG = PRED * C^T, so the loop carries only g (7 values per coordinate): b is
+// formed once per step (b = C^T g) for the error estimate, the position / velocity update and the next-step
+// prediction.  Per coordinate and substep that removes the (n-1)+1 b-update FMAs and 7 live registers; the e
+// coefficients (touched once per step) live in shared memory next to the rejected-step history.  The step
+// sequence, accept / reject rule and stopping rule are unchanged; results differ from the b-carrying form by
+// rounding only.
+#pragma once
+#include "rv_core.cuh"
+
+namespace rv {
+
+template <int VAR> RV_D double tPG(int n, int k) { if constexpr ((VAR & 2) != 0) return rvtabm::PG[n][k]; else return rvtab::PG[n][k]; }
+
+template <int P, int D, int PL, int VAR = 0>
+struct WalkerG : Walker<P, D, PL, VAR> {
+    using B = Walker<P, D, PL, VAR>;
+    static constexpr int NC = B::NC;
+    static constexpr int HIST = 21;   // doubles of shared-memory history per coordinate: er[7], br[7], e[7]
+    using B::x0; using B::v0; using B::a0; using B::ha0; using B::csx; using B::csv;
+    using B::b;                       // holds b between attempts and g inside the predictor-corrector loop
+    using B::t; using B::dt; using B::dt_last_done; using B::grp; using B::hist; using B::epsilon;
+    using B::star_in_norm; using B::n_force; using B::n_attempt;
+
+    template <int n>
+    RV_D void substep_g(bool commit, const double (&x0c)[NC], double (&xp)[NC], double (&at)[NC], double (&dg6)[NC]) {
+        const double dth = dt * tH<VAR>(n);
+        double xn[NC], an[NC];
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+            double p0 = fma(tPG<VAR>(n, 0), b[0][c], ha0[c]);
+            p0 = fma(tPG<VAR>(n, 1), b[1][c], p0);
+            p0 = fma(tPG<VAR>(n, 2), b[2][c], p0);
+            double p1 = tPG<VAR>(n, 3) * b[3][c];
+            p1 = fma(tPG<VAR>(n, 4), b[4][c], p1);
+            p1 = fma(tPG<VAR>(n, 5), b[5][c], p1);
+            p1 = fma(tPG<VAR>(n, 6), b[6][c], p1);
+            const double inner = fma(dth, p0 + p1, v0[c]);
+            xn[c] = fma(dth, inner, x0c[c]);
+        }
+        this->accel(xn, an);
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+            const double gk = an[c] - a0[c];
+            double s0 = gk * tGA<VAR>(n), s1 = 0.0;
+#pragma unroll
+            for (int i = 0; i < n - 1; i++) {
+                if (i & 1) s1 = fma(-b[i][c], tGB<VAR>(n, i), s1);
+                else s0 = fma(-b[i][c], tGB<VAR>(n, i), s0);
+            }
+            const double gn = s0 + s1;
+            if (n == 7) {
+                dg6[c] = sel(commit, gn - b[6][c], dg6[c]);
+                at[c] = sel(commit, an[c], at[c]);
+                xp[c] = sel(commit, xn[c], xp[c]);
+            }
+            b[n - 1][c] = sel(commit, gn, b[n - 1][c]);
+        }
+    }
+
+    RV_D void predict_g(double q, const double (&_e)[7], const double (&_b)[7], int c) {
+        double e[7];
+        if (q > 20.0) {
+#pragma unroll
+            for (int k = 0; k < 7; k++) { e[k] = 0.0; b[k][c] = 0.0; }
+        } else {
+            const double q1 = q, q2 = q1 * q1, q3 = q1 * q2, q4 = q2 * q2, q5 = q2 * q3, q6 = q3 * q3, q7 = q3 * q4;
+            e[0] = q1 * (_b[6] * 7.0 + _b[5] * 6.0 + _b[4] * 5.0 + _b[3] * 4.0 + _b[2] * 3.0 + _b[1] * 2.0 + _b[0]);
+            e[1] = q2 * (_b[6] * 21.0 + _b[5] * 15.0 + _b[4] * 10.0 + _b[3] * 6.0 + _b[2] * 3.0 + _b[1]);
+            e[2] = q3 * (_b[6] * 35.0 + _b[5] * 20.0 + _b[4] * 10.0 + _b[3] * 4.0 + _b[2]);
+            e[3] = q4 * (_b[6] * 35.0 + _b[5] * 15.0 + _b[4] * 5.0 + _b[3]);
+            e[4] = q5 * (_b[6] * 21.0 + _b[5] * 6.0 + _b[4]);
+            e[5] = q6 * (_b[6] * 7.0 + _b[5]);
+            e[6] = q7 * _b[6];
+#pragma unroll
+            for (int k = 0; k < 7; k++) b[k][c] = e[k] + (_b[k] - _e[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < 7; k++) hist.at((14 + k) * NC + c) = e[k];
+    }
+
+    // One IAS15 step attempt; same contract as Walker::attempt.
+    RV_D int attempt(bool active) {
+        warp_converge();
+        if (active) { n_attempt++; }
+        this->accel(x0, a0);
+        double x0c[NC];
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+            ha0[c] = 0.5 * a0[c];
+            x0c[c] = x0[c] - csx[c];
+            // g from b, in place (g_j needs b_k for k > j only)
+#pragma unroll
+            for (int j = 0; j < 7; j++) {
+                double s = 0.0;
+#pragma unroll
+                for (int k = 6; k > j; k--) s = fma(b[k][c], tDD<VAR>(k, j), s);
+                b[j][c] = s + b[j][c];
+            }
+        }
+        double xp[NC], at[NC], dg6[NC];
+#pragma unroll
+        for (int c = 0; c < NC; c++) { xp[c] = x0[c]; at[c] = a0[c]; dg6[c] = 0.0; }
+        double pc_err = 1e300, pc_last = 2.0;
+        int it = 0;
+        bool iterating = active;
+        while (true) {
+            if (iterating && (pc_err < 1e-16 || (it > 2 && pc_last <= pc_err) || it >= 12)) iterating = false;
+            if (!warp_any(iterating)) break;
+            if (iterating) { pc_last = pc_err; it++; }
+            substep_g<1>(iterating, x0c, xp, at, dg6);
+            substep_g<2>(iterating, x0c, xp, at, dg6);
+            substep_g<3>(iterating, x0c, xp, at, dg6);
+            substep_g<4>(iterating, x0c, xp, at, dg6);
+            substep_g<5>(iterating, x0c, xp, at, dg6);
+            substep_g<6>(iterating, x0c, xp, at, dg6);
+            substep_g<7>(iterating, x0c, xp, at, dg6);
+            double maxdg = 0.0, maxat = 0.0;
+#pragma unroll
+            for (int c = 0; c < NC; c++) {
+                const double ak = fabs(at[c]), dg = fabs(dg6[c]);
+                if (is_normal(ak) && ak > maxat) maxat = ak;
+                if (is_normal(dg) && dg > maxdg) maxdg = dg;
+            }
+            if (warp_any(star_in_norm)) {
+#pragma unroll
+                for (int d = 0; d < D; d++) {
+                    const double sa = fabs(this->template star_of<true>(at, d)), sg = fabs(this->template star_of<true>(dg6, d));
+                    if (star_in_norm && is_normal(sa) && sa > maxat) maxat = sa;
+                    if (star_in_norm && is_normal(sg) && sg > maxdg) maxdg = sg;
+                }
+            }
+            maxdg = grp.template gmax<true>(maxdg);
+            maxat = grp.template gmax<true>(maxat);
+            if (iterating) { pc_err = maxdg / maxat; n_force += 7; }
+        }
+        if (active) n_force += 1;
+        // b from g, in place (b_k needs g_j for j > k only)
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+#pragma unroll
+            for (int k = 0; k < 7; k++) {
+                double s = 0.0;
+#pragma unroll
+                for (int j = 6; j > k; j--) s = fma(b[j][c], tCC<VAR>(j, k), s);
+                b[k][c] = s + b[k][c];
+            }
+        }
+        // step-size control
+        double maxak = 0.0, maxb6 = 0.0;
+#pragma unroll
+        for (int pl = 0; pl < PL; pl++) {
+            double v2 = 0.0, x2 = 0.0;
+#pragma unroll
+            for (int d = 0; d < D; d++) { v2 = fma(v0[pl * D + d], v0[pl * D + d], v2); x2 = fma(xp[pl * D + d], xp[pl * D + d], x2); }
+            const bool keep = !(fabs(v2 * dt * dt / x2) < 1e-16);
+#pragma unroll
+            for (int d = 0; d < D; d++) {
+                const double ak = fabs(at[pl * D + d]), b6 = fabs(b[6][pl * D + d]);
+                if (keep && is_normal(ak) && ak > maxak) maxak = ak;
+                if (keep && is_normal(b6) && b6 > maxb6) maxb6 = b6;
+            }
+        }
+        if (warp_any(star_in_norm)) {
+            double v2 = 0.0, x2 = 0.0, sa[D], sb[D];
+#pragma unroll
+            for (int d = 0; d < D; d++) {
+                const double sv = this->template star_of<true>(v0, d), sx = this->template star_of<true>(xp, d);
+                v2 = fma(sv, sv, v2); x2 = fma(sx, sx, x2);
+                sa[d] = fabs(this->template star_of<true>(at, d)); sb[d] = fabs(this->template star_of<true>(b[6], d));
+            }
+            const bool keep = star_in_norm && !(fabs(v2 * dt * dt / x2) < 1e-16);
+#pragma unroll
+            for (int d = 0; d < D; d++) {
+                if (keep && is_normal(sa[d]) && sa[d] > maxak) maxak = sa[d];
+                if (keep && is_normal(sb[d]) && sb[d] > maxb6) maxb6 = sb[d];
+            }
+        }
+        maxak = grp.template gmax<true>(maxak);
+        maxb6 = grp.template gmax<true>(maxb6);
+        int result = 0;
+        if (active) {
+            const double err = maxb6 / maxak;
+            const double dt_done = dt;
+            double dt_new;
+            if (is_normal(err)) dt_new = pow(epsilon / err, 1.0 / 7.0) * dt_done;
+            else dt_new = dt_done / 0.25;
+            if (fabs(dt_new / dt_done) < 0.25) {
+                dt = dt_new;
+                if (dt_last_done != 0.0) {
+                    const double q = dt / dt_last_done;
+#pragma unroll
+                    for (int c = 0; c < NC; c++) {
+                        double _e[7], _b[7];
+#pragma unroll
+                        for (int k = 0; k < 7; k++) { _e[k] = hist.at(k * NC + c); _b[k] = hist.at((7 + k) * NC + c); }
+                        predict_g(q, _e, _b, c);
+                    }
+                } else {
+                    // no history yet: rebound retries with the b it holds (the corrected ones)
+                }
+            } else {
+                if (fabs(dt_new / dt_done) > 1.0 && dt_new / dt_done > 4.0) dt_new = dt_done / 0.25;
+                dt = dt_new;
+                const double dt2 = dt_done * dt_done;
+#pragma unroll
+                for (int c = 0; c < NC; c++) {
+                    {
+                        const double a = x0[c];
+                        double s = b[6][c] * (1. / 72.);
+                        s = fma(b[5][c], 1. / 56., s); s = fma(b[4][c], 1. / 42., s); s = fma(b[3][c], 1. / 30., s);
+                        s = fma(b[2][c], 1. / 20., s); s = fma(b[1][c], 1. / 12., s); s = fma(b[0][c], 1. / 6., s);
+                        s = fma(a0[c], 0.5, s);
+                        csx[c] += fma(s, dt2, v0[c] * dt_done);
+                        x0[c] = a + csx[c];
+                        csx[c] += a - x0[c];
+                    }
+                    {
+                        const double a = v0[c];
+                        double s = b[6][c] * (1. / 8.);
+                        s = fma(b[5][c], 1. / 7., s); s = fma(b[4][c], 1. / 6., s); s = fma(b[3][c], 1. / 5., s);
+                        s = fma(b[2][c], 1. / 4., s); s = fma(b[1][c], 1. / 3., s); s = fma(b[0][c], 1. / 2., s);
+                        s += a0[c];
+                        csv[c] = fma(s, dt_done, csv[c]);
+                        v0[c] = a + csv[c];
+                        csv[c] += a - v0[c];
+                    }
+                }
+                t += dt_done;
+                dt_last_done = dt_done;
+                const double q = dt / dt_done;
+#pragma unroll
+                for (int c = 0; c < NC; c++) {
+                    double _e[7], _b[7];
+#pragma unroll
+                    for (int k = 0; k < 7; k++) {
+                        _e[k] = hist.at((14 + k) * NC + c); _b[k] = b[k][c];
+                        hist.at(k * NC + c) = _e[k]; hist.at((7 + k) * NC + c) = _b[k];
+                    }
+                    predict_g(q, _e, _b, c);
+                }
+                result = 1;
+            }
+        }
+        warp_converge();
+        if (this->template encounter<true>()) result |= 2;
+        return result;
+    }
+
+};
+
+}  // namespace rv

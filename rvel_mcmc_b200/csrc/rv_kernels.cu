@@ -2,12 +2,14 @@
 //
 // loglik_kernel: persistent grid (resident CTAs x SM count); every lane group pulls (walker, leg)
 // items from a global counter and runs the IAS15 state machine of rv_loglik.cuh.  Observation epochs,
-// velocities and errors are staged once per CTA into shared memory; the rejected-step history (br/er)
-// lives in shared memory, strided per lane; everything else of the walker state is in registers.
+// velocities and errors are staged once per CTA into shared memory; the once-per-step coefficients (e, and the
+// rejected-step history br/er) live in shared memory, strided per lane; x0, v0, a0, the carries and the seven g
+// coefficients per coordinate are in registers.
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include "rv_launch.h"
 #include "rv_loglik.cuh"
+#include "rv_core_g.cuh"
 
 namespace rv {
 
@@ -25,7 +27,7 @@ struct DevAll {
     __device__ __forceinline__ bool operator()(bool f) const { return __all_sync(0xffffffffu, f) != 0; }
 };
 
-template <int P, int D, int PL, int NT, int MINB>
+template <int P, int D, int PL, int NT, int MINB, int VAR>
 __global__ void __launch_bounds__(NT, MINB) loglik_kernel(const LoglikArgs a) {
     extern __shared__ double sm[];
     const int nobs = a.nf + a.nb;
@@ -39,7 +41,7 @@ __global__ void __launch_bounds__(NT, MINB) loglik_kernel(const LoglikArgs a) {
         serr[i] = a.oerr[i];
     }
     __syncthreads();
-    using W = Walker<P, D, PL>;
+    using W = WalkerG<P, D, PL, VAR>;
     W w;
     const int lane = threadIdx.x & 31;
     w.grp.init(lane);
@@ -66,12 +68,13 @@ __global__ void finalize_kernel(const double* __restrict__ part_chi2, const int*
 
 __global__ void curve_finalize_kernel(unsigned long long* item_counter) { *item_counter = 0ull; }
 
-template <int P, int D, int PL, int NT, int MINB>
+template <int P, int D, int PL, int NT, int MINB, int VAR = 0>
 static cudaError_t launch_one(const LoglikArgs& a, int num_sms, cudaStream_t stream) {
-    auto kern = loglik_kernel<P, D, PL, NT, MINB>;
+    auto kern = loglik_kernel<P, D, PL, NT, MINB, VAR>;
     const int nobs = a.nf + a.nb;
     constexpr int NC = PL * D;
-    const size_t smem = sizeof(double) * ((size_t)3 * nobs + (size_t)14 * NC * NT);
+    constexpr int W21 = WalkerG<P, D, PL, VAR>::HIST;
+    const size_t smem = sizeof(double) * ((size_t)3 * nobs + (size_t)W21 * NC * NT);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int occ = 0;

@@ -33,8 +33,8 @@ struct LoglikArgs {
 enum : int { PH_NEED_ITEM = 0, PH_ENTRY, PH_CHECK, PH_STEP, PH_DONE };
 
 // Fetch / WarpAll are policy objects: device = atomicAdd + shuffle / __all_sync, host mirror = trivial.
-template <int P, int D, int PL, class Fetch, class WarpAll>
-RV_D void run_items(Walker<P, D, PL>& w, const LoglikArgs& a, const double* st, const double* srv,
+template <class WK, class Fetch, class WarpAll>
+RV_D void run_items(WK& w, const LoglikArgs& a, const double* st, const double* srv,
                     const double* serr, Fetch& fetch, WarpAll& warp_all, bool lane_active) {
     const bool curve = (a.times != nullptr);
     const long long n_items = curve ? a.W : 2 * a.W;

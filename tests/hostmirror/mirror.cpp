@@ -6,6 +6,7 @@
 #include <string.h>
 #include <vector>
 #include "../../rvel_mcmc_b200/csrc/rv_loglik.cuh"
+#include "../../rvel_mcmc_b200/csrc/rv_core_g.cuh"
 #include "../../rvel_mcmc_b200/csrc/rv_model.h"
 
 namespace {
@@ -15,15 +16,20 @@ struct HostFetch {
 };
 struct HostAll { bool operator()(bool f) const { return f; } };
 
-template <int P, int D>
-void run(const rv::LoglikArgs& a) {
-    rv::Walker<P, D, P> w;
+template <class WK, int NCOORD>
+void run_with(const rv::LoglikArgs& a) {
+    WK w;
     w.grp.init(0);
-    std::vector<double> hist(14 * P * D, 0.0);
+    std::vector<double> hist(21 * NCOORD, 0.0);
     w.hist.p = hist.data(); w.hist.stride = 1;
     HostFetch f{a.item_counter};
     HostAll all;
     rv::run_items(w, a, a.ot, a.orv, a.oerr, f, all, true);
+}
+
+template <int P, int D>
+void run(const rv::LoglikArgs& a) {
+    run_with<rv::WalkerG<P, D, P, 0>, P * D>(a);
 }
 }  // namespace
 
