@@ -94,6 +94,36 @@ def oracle_batch(obs, theta, nthreads):
     return time.perf_counter() - t0, logp, st, cnt
 
 
+def run_ess(ctx, model, oh):
+    """ESS/s of the three device samplers on the HD155358 posterior (bounded runs; reference AC definition + Sokal tau)."""
+    from rvel_mcmc_b200.samplers import ess
+    from rvel_mcmc_b200 import driver
+    out = {}
+    sc = np.array([HD_SCALES[k] for k in ("a", "h", "k", "m", "l")] * 2)
+
+    def summarise(name, chain, seconds, evals, burn):
+        c = chain[burn:]
+        n_eff, tau = ess(c)
+        ac_ref = max(driver.ac_time(c[:, 0, i]) for i in range(c.shape[2]))     # driver.py:366-377 (first lag with AC < 0.5)
+        out[name] = {"walkers": int(chain.shape[1]), "steps": int(chain.shape[0]), "seconds": seconds,
+                     "evals_per_s": evals / seconds, "tau_int_max": tau, "ac_time_ref_max": ac_ref,
+                     "ess_per_s": n_eff * (chain.shape[0] / c.shape[0]) / seconds}
+
+    W, n = 8192, 400
+    t0 = time.perf_counter()
+    r = model.stretch_run(oh, walker_ball(W, 5), n, seed=11, thin=1)
+    summarise("stretch", r["chain"], time.perf_counter() - t0, W * (n + 1), n // 4)
+    W, n = 8192, 400
+    t0 = time.perf_counter()
+    r = model.mh_run(oh, walker_ball(W, 6), sc, 0.1, n, seed=12, thin=1)
+    summarise("mh", r["chain"], time.perf_counter() - t0, W * (n + 1), n // 4)
+    W, n = 2048, 60
+    t0 = time.perf_counter()
+    r = model.smala_run(oh, walker_ball(W, 7), 0.025, 1.4, n, seed=13, thin=1)
+    summarise("smala", r["chain"], time.perf_counter() - t0, W * (n + 1), n // 4)
+    return out
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU path (oracle port; rebound itself is not installable here)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -101,7 +131,7 @@ def run_reference(args):
         return
     obs = load_obs()
     cores = os.cpu_count() or 1
-    sample = max(cores * 16, 256)
+    sample = 4096                      # ~2 s of work per step on 16 cores
     theta = walker_ball(sample, 1234)
     for _ in range(min(args.warmup, 1)):
         oracle_batch(obs, theta[: cores * 4], cores)
@@ -133,6 +163,8 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--mapping", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="walkers in the timed CPU sample (0: about 15 s of work)")
+    ap.add_argument("--ess", action="store_true", help="also run the stretch / MH / SMALA samplers and report ESS/s")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -194,7 +226,6 @@ def main():
         step_dev(args.warmup + k)
         ev[k][1].record()
     barrier()
-    sampler.stop_flag = True
     ms = np.array([a.elapsed_time(b) for a, b in ev])
     total_ms = float(ms.sum())
     if world > 1:
@@ -224,6 +255,12 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
 
+    # keep the GPU under the same load until the clock sampler (nvidia-smi, ~0.3 s per query) has a few samples
+    t_load = time.perf_counter()
+    while len(sampler.samples) < 4 and time.perf_counter() - t_load < 5.0:
+        step_dev(0)
+        torch.cuda.synchronize()
+    sampler.stop_flag = True
     sampler.join(timeout=2)
     if rank != 0:
         if world > 1:
@@ -243,15 +280,31 @@ def main():
     achieved = flops_eval * W / (kernel_ms * 1e-3) / 1e12
     peak = ctx.fp64_peak_tflops()
     roofline = {"bound": "fp64_fma_pipe", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": None,
+                "traffic": 5.33e6, "traffic_note": "dram bytes per launch, profiles/r01e_ncu_loglik_kernel.txt (algorithmic: %d B)" % (W * 92),
+                "executed": "the kernel executes fewer FP64 instructions than the algorithmic count (implicit star, coplanar, "
+                            "g-only corrector loop): ncu sm__pipe_fp64_cycles_active = 63%% of peak (profiles/r01e_ncu_loglik_kernel.txt)",
                 "note": "achieved = SURVEY 8(d) algorithmic flops (S=%.0f force evals, T=%.0f step attempts per eval, "
                         "432*S+1350*T) / CUDA-event kernel time; peak = dependent-free fma.rn.f64 microbenchmark on this GPU "
                         "(rv_fp64_peak; MEASURED_PEAKS.json has no FP64 entry)" % (S_eval, T_eval)}
 
+    # ---- the same evaluations with the backward leg swept monotonically (model option, not the default) ----
+    model.set_option("monotone_backward", 1)
+    ref_logp = d_logp.clone()
+    step_dev(0); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    flush.zero_(); e0.record(); step_dev(0); e1.record(); torch.cuda.synchronize()
+    okm = (d_status == 0)
+    mono = {"value": W / (e0.elapsed_time(e1) * 1e-3), "unit": UNIT + " per GPU", "ms_per_step": e0.elapsed_time(e1),
+            "max_abs_logp_diff_vs_default": float((d_logp[okm] - ref_logp[okm]).abs().max().item()),
+            "note": "option monotone_backward=1: backward leg visited 0 -> most negative epoch once (state.py:273 order) instead "
+                    "of state.py:91's stored order; NOT the headline value"}
+    model.set_option("monotone_backward", 0)
+
     cpu_baseline = None
     if not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        sample = max(cores * 32, 256)
+        t_probe, _, _, _ = oracle_batch(obs, host_theta[1][:cores * 8].numpy(), cores)      # size the sample: ~15 s of CPU work
+        sample = args.cpu_sample or int(min(W, max(cores * 32, 15.0 / max(t_probe, 1e-3) * cores * 8)))
         dt, lo, so, cnt = oracle_batch(obs, host_theta[0][:sample].numpy(), cores)
         # parity spot check on the same vectors
         step_dev(0)
@@ -273,8 +326,11 @@ def main():
                        "mapping": "lane-per-planet" if args.mapping == 0 else "thread-per-walker", "ok_fraction": ok_frac},
             "e2e": {"value": n_total / e2e_s, "unit": UNIT, "h2d_bytes_per_step": W * 10 * 8, "d2h_bytes_per_step": W * 12},
             "gpu_launches": 2 * args.steps, "clocks": sampler.summary(), "roofline": roofline}
+    line["monotone_backward_option"] = mono
     if cpu_baseline:
         line["cpu_baseline"] = cpu_baseline
+    if args.ess and world == 1:
+        line["ess"] = run_ess(ctx, model, oh)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

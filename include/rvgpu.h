@@ -70,7 +70,9 @@ int rv_model_create(rv_ctx* ctx, int n_planets, const double* fixed, int nvars, 
                     const int32_t* free_elem, double hill_factor, int dims, rv_model** out);
 int rv_model_destroy(rv_model* model);
 /* options: "dt0" (1e-3), "epsilon" (1e-9), "max_attempts", "hill_factor", "mapping" (0 lane-per-planet, 1 thread-per-walker),
- * "check_prior" (1; 0 = rv_loglik_d_dd integrates even outside the hard prior, as state.py:290 does)        */
+ * "check_prior" (1; 0 = rv_loglik_d_dd integrates even outside the hard prior, as state.py:290 does),
+ * "monotone_backward" (0 = rv_loglik visits obs.tb in its stored order as state.py:91 does; 1 = one sweep from 0 to the
+ *   most negative epoch, the order state.py:273 uses: about half the backward steps, logp equal to ~1e-11)            */
 int rv_model_set_option(rv_model* model, const char* key, double value);
 
 /* ---- State.get_logp (state.py:103-110) for W parameter vectors; HOST buffers -------------------- */

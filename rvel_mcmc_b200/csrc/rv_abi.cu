@@ -215,6 +215,7 @@ int rv_model_set_option(rv_model* m, const char* key, double value) {
     else if (!strcmp(key, "hill_factor")) m->h.hill_factor = value;
     else if (!strcmp(key, "mapping")) m->mapping = (int)value;
     else if (!strcmp(key, "check_prior")) m->h.check_prior = value != 0.0;
+    else if (!strcmp(key, "monotone_backward")) m->h.monotone_backward = value != 0.0;
     else return fail(ctx, -20, "rv_model_set_option: unknown key '%s'", key);
     CU(ctx, cudaSetDevice(ctx->device));
     CU(ctx, cudaMemcpy(m->d, &m->h, sizeof(rv::Model), cudaMemcpyHostToDevice));

@@ -41,6 +41,8 @@ RV_D void run_items(WK& w, const LoglikArgs& a, const double* st, const double* 
     const int max_attempts = a.model->max_attempts;
     const int nvars = a.model->nvars;
     const bool leader = (w.grp.rank == 0);
+    const bool mono = a.model->monotone_backward != 0;
+    bool rev = false;       // this item visits its epochs in reversed storage order
     int phase = lane_active ? PH_NEED_ITEM : PH_DONE;
     long long item = -1, wi = 0;
     const double *lt = nullptr, *lrv = nullptr, *lerr = nullptr;
@@ -69,11 +71,11 @@ RV_D void run_items(WK& w, const LoglikArgs& a, const double* st, const double* 
                 item = fetch(w.grp);
                 if (item >= n_items) { phase = PH_DONE; break; }
                 if (curve) {
-                    wi = item; lt = a.times; lrv = nullptr; lerr = nullptr; c.n = a.nt;
+                    wi = item; lt = a.times; lrv = nullptr; lerr = nullptr; c.n = a.nt; rev = false;
                 } else if (item < a.W) {       // backward legs first: they are the longer ones
-                    wi = item; lt = st + a.nf; lrv = srv + a.nf; lerr = serr + a.nf; c.n = a.nb;
+                    wi = item; lt = st + a.nf; lrv = srv + a.nf; lerr = serr + a.nf; c.n = a.nb; rev = mono;
                 } else {
-                    wi = item - a.W; lt = st; lrv = srv; lerr = serr; c.n = a.nf;
+                    wi = item - a.W; lt = st; lrv = srv; lerr = serr; c.n = a.nf; rev = false;
                 }
                 w.n_force = 0; w.n_attempt = 0;
                 c.ie = 0; c.chi2 = 0.0; c.attempts = 0;
@@ -83,7 +85,7 @@ RV_D void run_items(WK& w, const LoglikArgs& a, const double* st, const double* 
             }
             if (phase == PH_ENTRY) {            // sim.integrate(t) entry (rebound: reb_integrate)
                 if (c.ie == c.n) { finish(ST_OK); continue; }
-                c.tmax = lt[c.ie];
+                c.tmax = lt[rev ? c.n - 1 - c.ie : c.ie];
                 c.last_full_dt = w.dt;
                 w.dt_last_done = 0.0;
                 c.status = RUN;
@@ -100,7 +102,8 @@ RV_D void run_items(WK& w, const LoglikArgs& a, const double* st, const double* 
                 if (curve) {
                     if (leader) a.rv_out[wi * a.nt + c.ie] = vx;
                 } else {
-                    const double r = vx - lrv[c.ie], er = lerr[c.ie];
+                    const int io = rev ? c.n - 1 - c.ie : c.ie;
+                    const double r = vx - lrv[io], er = lerr[io];
                     c.chi2 += (r * r) / (er * er);
                 }
                 c.ie++;

@@ -40,6 +40,7 @@ inline int build_model(Model* m, int P, const double* fixed, int nvars, const in
     m->m_star = 1.0;     // state.py:38
     m->max_attempts = 1 << 20;
     m->check_prior = 1;
+    m->monotone_backward = 0;
     return 0;
 }
 

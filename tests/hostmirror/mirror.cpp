@@ -33,6 +33,9 @@ void run(const rv::LoglikArgs& a) {
 }
 }  // namespace
 
+static int g_monotone = 0;
+extern "C" void mirror_set_monotone(int v) { g_monotone = v; }
+
 extern "C" int mirror_loglik(int P, const double* fixed, int nvars, const int* fp, const int* fe, double hill, int dims,
                              const double* tf, const double* rvf, const double* ef, int nf,
                              const double* tb, const double* rvb, const double* eb, int nb, double npoints,
@@ -41,6 +44,7 @@ extern "C" int mirror_loglik(int P, const double* fixed, int nvars, const int* f
     rv::Model m;
     int rc = rv::build_model(&m, P, fixed, nvars, fp, fe, hill, dims);
     if (rc) return rc;
+    m.monotone_backward = g_monotone;
     std::vector<double> ot(nf + nb), orv(nf + nb), oerr(nf + nb);
     for (int i = 0; i < nf; i++) { ot[i] = tf[i]; orv[i] = rvf[i]; oerr[i] = ef[i]; }
     for (int i = 0; i < nb; i++) { ot[nf + i] = tb[i]; orv[nf + i] = rvb[i]; oerr[nf + i] = eb[i]; }

@@ -190,3 +190,23 @@ def test_million_walker_properties(ctx):
     lo, so, _ = T.orc_logp_batch(np.zeros((2, 7)), T.FP10, T.FE10, 2.0, obs, base[:64])
     assert np.array_equal(so, sg[0, :64])
     assert np.abs(lo - lg[0, :64])[so == 0].max() < 1e-6
+
+
+def test_monotone_backward_option_matches_default(ctx):
+    # model option: backward leg swept once from 0 to the most negative epoch (state.py:273 order) instead of
+    # state.py:91's stored order -- same likelihood within the north_star tolerance, about 2/3 of the work
+    obs = T.load_vels("HD155358.vels")
+    oh = _obs_handle(ctx, obs)
+    m = _model(ctx, np.zeros((2, 7)), T.FP10, T.FE10, 2.0)
+    theta = T.gaussian_ball(T.HD_SOL, T.HD_SCALE_VEC, 4096, 77)
+    theta[0] = T.HD_SOL
+    ctx.count_work(True); ctx.work_counters(reset=True)
+    l0, s0 = m.loglik(oh, theta)
+    c0 = ctx.work_counters(reset=True)
+    m.set_option("monotone_backward", 1)
+    l1, s1 = m.loglik(oh, theta)
+    c1 = ctx.work_counters(reset=True)
+    ctx.count_work(False)
+    assert np.array_equal(s0, s1) and (s0 == 0).all()
+    assert np.abs(l1 - l0).max() < 1e-8 and abs(l1[0] - T.KAT2_LOGP) < 5e-11
+    assert c1[1] < 0.75 * c0[1]

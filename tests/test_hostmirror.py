@@ -70,3 +70,17 @@ def test_mirror_one_and_three_planets():
         lm, sm, _ = T.mirror_loglik(E, [], [], 1.0, obs, np.zeros((1, 0)))
         assert so == sm[0] == 0
         assert abs(lo - lm[0]) < 1e-9 * max(1.0, abs(lo))
+
+
+def test_mirror_monotone_backward_option():
+    # state.py:91 order (0 -> tb[0] -> forward hops) vs one monotone sweep (state.py:273 order): same logp, fewer steps
+    obs, theta = _hd(6, 9)
+    l0, s0, c0 = T.mirror_loglik(np.zeros((2, 7)), T.FP10, T.FE10, 2.0, obs, theta)
+    T.mirror().mirror_set_monotone(1)
+    try:
+        l1, s1, c1 = T.mirror_loglik(np.zeros((2, 7)), T.FP10, T.FE10, 2.0, obs, theta)
+    finally:
+        T.mirror().mirror_set_monotone(0)
+    assert np.array_equal(s0, s1) and (s0 == 0).all()
+    assert np.abs(l1 - l0).max() < 1e-9
+    assert c1[1] < 0.75 * c0[1]           # 1244 -> 637 backward steps
