@@ -63,9 +63,9 @@ struct VarThread {
     int tid, set, planet, order;   // order: 0 real, 1 first, 2 second, -1 idle
     int sa, sb;                    // parent sets (first-order sets of parameters pa, pb)
     int pa, pb;                    // parameter indices (pa >= pb)
-    double x0[D], v0[D], a0[D], ha0[D], csx[D], csv[D];
-    double b[7][D], g[7][D];
-    double xn[D], at[D], dg6[D];   // last predictor position, last force, last change of b6
+    double x0[D], v0[D], a0[D], ha0[D], csx[D], csv[D], x0c[D];
+    double q[7][D];                // b coefficients between step attempts, g coefficients inside the predictor-corrector loop
+    double xn[D], at[D], dg6[D];   // last predictor position, last force, last change of g6 (= b6)
     double acc;                    // planet-0 thread of a set: running chi2 / d[a] / dd[a][b]
 };
 
@@ -243,47 +243,61 @@ RV_D void var_predict(double q, const double (&_e)[7], const double (&_b)[7], do
     for (int k = 0; k < 7; k++) b[k][c] = e[k] + be[k];
 }
 
-// One Gauss-Radau substep, first half: predicted position at h_n, published to the exchange buffer.
-template <int n, int P, int D>
-RV_D void var_substep_predict(VarThread<P, D>& th, double dt, double* __restrict__ Xw) {
-    const double dth = dt * rvtab::H[n];
+// One Gauss-Radau substep, first half: predicted position at h_n from the g coefficients (PG = PRED * C^T),
+// published to the exchange buffer.  n is a RUNTIME index: the substep loop is not unrolled, so the force code
+// exists once in the instruction stream (the unrolled form thrashed the instruction cache: 2.6 stall cycles per
+// issued instruction on no_instruction, profiles/r01g_ncu_var_kernel.txt).
+template <int P, int D>
+RV_D void var_substep_predict(VarThread<P, D>& th, int n, double dt, double* __restrict__ Xw) {
+    const double dth = dt * rvtabm::H[n];
+    const double c0 = rvtabm::PG[n][0], c1 = rvtabm::PG[n][1], c2 = rvtabm::PG[n][2], c3 = rvtabm::PG[n][3],
+                 c4 = rvtabm::PG[n][4], c5 = rvtabm::PG[n][5], c6 = rvtabm::PG[n][6];
 #pragma unroll
     for (int c = 0; c < D; c++) {
-        double p0 = fma(rvtab::PRED[n][0], th.b[0][c], th.ha0[c]);
-        p0 = fma(rvtab::PRED[n][1], th.b[1][c], p0);
-        p0 = fma(rvtab::PRED[n][2], th.b[2][c], p0);
-        double p1 = rvtab::PRED[n][3] * th.b[3][c];
-        p1 = fma(rvtab::PRED[n][4], th.b[4][c], p1);
-        p1 = fma(rvtab::PRED[n][5], th.b[5][c], p1);
-        p1 = fma(rvtab::PRED[n][6], th.b[6][c], p1);
+        double p0 = fma(c0, th.q[0][c], th.ha0[c]);
+        p0 = fma(c1, th.q[1][c], p0);
+        p0 = fma(c2, th.q[2][c], p0);
+        double p1 = c3 * th.q[3][c];
+        p1 = fma(c4, th.q[4][c], p1);
+        p1 = fma(c5, th.q[5][c], p1);
+        p1 = fma(c6, th.q[6][c], p1);
         const double inner = fma(dth, p0 + p1, th.v0[c]);
-        th.xn[c] = th.x0[c] + fma(dth, inner, -th.csx[c]);
+        th.xn[c] = fma(dth, inner, th.x0c[c]);
         Xw[(th.set * P + th.planet) * D + c] = th.xn[c];
     }
 }
 
-// Second half: force at the predicted positions, g_{n-1} and b update.
+// Second half: g_{n-1} from the force at the predicted positions (static n: the g chain indexes registers).
 template <int n, int P, int D>
-RV_D void var_substep_update(VarThread<P, D>& th, const double* __restrict__ Xr, const double* __restrict__ dm,
-                             const VarUniform<P>& u) {
-    double an[D];
-    var_force(th, Xr, dm, u, an);
+RV_D void var_substep_corrector(VarThread<P, D>& th, const double (&an)[D]) {
 #pragma unroll
     for (int c = 0; c < D; c++) {
         const double gk = an[c] - th.a0[c];
         double s0 = gk * rvtab::GA[n], s1 = 0.0;
 #pragma unroll
         for (int i = 0; i < n - 1; i++) {
-            if (i & 1) s1 = fma(-th.g[i][c], rvtab::GB[n][i], s1);
-            else s0 = fma(-th.g[i][c], rvtab::GB[n][i], s0);
+            if (i & 1) s1 = fma(-th.q[i][c], rvtab::GB[n][i], s1);
+            else s0 = fma(-th.q[i][c], rvtab::GB[n][i], s0);
         }
         const double gn = s0 + s1;
-        const double tmp = gn - th.g[n - 1][c];
-        th.g[n - 1][c] = gn;
-#pragma unroll
-        for (int i = 0; i < n - 1; i++) th.b[i][c] = fma(tmp, rvtab::CC[n - 1][i], th.b[i][c]);
-        th.b[n - 1][c] += tmp;
-        if (n == 7) { th.dg6[c] = tmp; th.at[c] = an[c]; }
+        if (n == 7) { th.dg6[c] = gn - th.q[6][c]; th.at[c] = an[c]; }
+        th.q[n - 1][c] = gn;
+    }
+}
+
+template <int P, int D>
+RV_D void var_substep_update(VarThread<P, D>& th, int n, const double* __restrict__ Xr, const double* __restrict__ dm,
+                             const VarUniform<P>& u) {
+    double an[D];
+    var_force(th, Xr, dm, u, an);
+    switch (n) {
+        case 1: var_substep_corrector<1>(th, an); break;
+        case 2: var_substep_corrector<2>(th, an); break;
+        case 3: var_substep_corrector<3>(th, an); break;
+        case 4: var_substep_corrector<4>(th, an); break;
+        case 5: var_substep_corrector<5>(th, an); break;
+        case 6: var_substep_corrector<6>(th, an); break;
+        default: var_substep_corrector<7>(th, an); break;
     }
 }
 
@@ -463,10 +477,10 @@ RV_D void var_run_items(Exec& ex, const VarArgs& a, const VarLayout& L, double* 
 #pragma unroll
                 for (int c = 0; c < D; c++) {
                     th.csx[c] = 0.0; th.csv[c] = 0.0; th.a0[c] = 0.0; th.ha0[c] = 0.0;
-                    th.xn[c] = th.x0[c]; th.at[c] = 0.0; th.dg6[c] = 0.0;
+                    th.xn[c] = th.x0[c]; th.at[c] = 0.0; th.dg6[c] = 0.0; th.x0c[c] = th.x0[c];
 #pragma unroll
                     for (int k = 0; k < 7; k++) {
-                        th.b[k][c] = 0.0; th.g[k][c] = 0.0;
+                        th.q[k][c] = 0.0;
                         esm[(k * D + c) * NT + th.tid] = 0.0;
                         hist[(k * D + c) * NT + th.tid] = 0.0;
                         hist[((7 + k) * D + c) * NT + th.tid] = 0.0;
@@ -491,12 +505,14 @@ RV_D void var_run_items(Exec& ex, const VarArgs& a, const VarLayout& L, double* 
 #pragma unroll
                     for (int cc = 0; cc < D; cc++) {
                         th.ha0[cc] = 0.5 * th.a0[cc];
+                        th.x0c[cc] = th.x0[cc] - th.csx[cc];
+                        // g from b, in place (g_j needs b_k for k > j only)
 #pragma unroll
                         for (int j = 0; j < 7; j++) {
                             double s = 0.0;
 #pragma unroll
-                            for (int k = 6; k > j; k--) s = fma(th.b[k][cc], rvtab::DD[k][j], s);
-                            th.g[j][cc] = s + th.b[j][cc];
+                            for (int k = 6; k > j; k--) s = fma(th.q[k][cc], rvtab::DD[k][j], s);
+                            th.q[j][cc] = s + th.q[j][cc];
                         }
                     }
                 });
@@ -508,17 +524,14 @@ RV_D void var_run_items(Exec& ex, const VarArgs& a, const VarLayout& L, double* 
                     if (pc_err < 1e-16 || (it > 2 && pc_last <= pc_err) || it >= 12) break;
                     pc_last = pc_err;
                     it++;
-#define RV_VAR_SUBSTEP(N)                                                                                        \
-    {                                                                                                            \
-        double* Xw = pos + buf * L.npos;                                                                         \
-        ex.each([&](VarThread<P, D>& th) { if (th.order >= 0) var_substep_predict<N>(th, dt, Xw); });            \
-        ex.sync();                                                                                               \
-        ex.each([&](VarThread<P, D>& th) { if (th.order >= 0) var_substep_update<N>(th, Xw, dm, u); });          \
-        buf ^= 1;                                                                                                \
-    }
-                    RV_VAR_SUBSTEP(1) RV_VAR_SUBSTEP(2) RV_VAR_SUBSTEP(3) RV_VAR_SUBSTEP(4)
-                    RV_VAR_SUBSTEP(5) RV_VAR_SUBSTEP(6) RV_VAR_SUBSTEP(7)
-#undef RV_VAR_SUBSTEP
+#pragma unroll 1
+                    for (int n = 1; n <= 7; n++) {
+                        double* Xw = pos + buf * L.npos;
+                        ex.each([&](VarThread<P, D>& th) { if (th.order >= 0) var_substep_predict(th, n, dt, Xw); });
+                        ex.sync();
+                        ex.each([&](VarThread<P, D>& th) { if (th.order >= 0) var_substep_update(th, n, Xw, dm, u); });
+                        buf ^= 1;
+                    }
                     // convergence monitor over every coordinate: max |change of b6| / max |a|
                     ex.each([&](VarThread<P, D>& th) {
                         double mg = 0.0, ma = 0.0;
@@ -539,9 +552,21 @@ RV_D void var_run_items(Exec& ex, const VarArgs& a, const VarLayout& L, double* 
                     n_force += 7;
                 }
                 n_force += 1;
-                // step-size control over the real particles
+                // b from g, in place (b_k needs g_j for j > k only); then step-size control over the real particles
                 ex.each([&](VarThread<P, D>& th) {
                     double mb = 0.0, ma = 0.0;
+                    if (th.order >= 0) {
+#pragma unroll
+                        for (int cc = 0; cc < D; cc++) {
+#pragma unroll
+                            for (int k = 0; k < 7; k++) {
+                                double s = 0.0;
+#pragma unroll
+                                for (int j = 6; j > k; j--) s = fma(th.q[j][cc], rvtab::CC[j][k], s);
+                                th.q[k][cc] = s + th.q[k][cc];
+                            }
+                        }
+                    }
                     if (th.order == 0) {
                         double v2 = 0.0, x2 = 0.0;
 #pragma unroll
@@ -549,7 +574,7 @@ RV_D void var_run_items(Exec& ex, const VarArgs& a, const VarLayout& L, double* 
                         const bool keep = !(fabs(v2 * dt * dt / x2) < 1e-16);
 #pragma unroll
                         for (int cc = 0; cc < D; cc++) {
-                            const double ak = fabs(th.at[cc]), b6 = fabs(th.b[6][cc]);
+                            const double ak = fabs(th.at[cc]), b6 = fabs(th.q[6][cc]);
                             if (keep && is_normal(ak) && ak > ma) ma = ak;
                             if (keep && is_normal(b6) && b6 > mb) mb = b6;
                         }
@@ -579,7 +604,7 @@ RV_D void var_run_items(Exec& ex, const VarArgs& a, const VarLayout& L, double* 
                                     _e[k] = hist[(k * D + cc) * NT + th.tid];
                                     _b[k] = hist[((7 + k) * D + cc) * NT + th.tid];
                                 }
-                                var_predict<D>(q, _e, _b, e, th.b, cc);
+                                var_predict<D>(q, _e, _b, e, th.q, cc);
 #pragma unroll
                                 for (int k = 0; k < 7; k++) esm[(k * D + cc) * NT + th.tid] = e[k];
                             }
@@ -596,9 +621,9 @@ RV_D void var_run_items(Exec& ex, const VarArgs& a, const VarLayout& L, double* 
                         for (int cc = 0; cc < D; cc++) {
                             {
                                 const double x = th.x0[cc];
-                                double s = th.b[6][cc] * (1. / 72.);
-                                s = fma(th.b[5][cc], 1. / 56., s); s = fma(th.b[4][cc], 1. / 42., s); s = fma(th.b[3][cc], 1. / 30., s);
-                                s = fma(th.b[2][cc], 1. / 20., s); s = fma(th.b[1][cc], 1. / 12., s); s = fma(th.b[0][cc], 1. / 6., s);
+                                double s = th.q[6][cc] * (1. / 72.);
+                                s = fma(th.q[5][cc], 1. / 56., s); s = fma(th.q[4][cc], 1. / 42., s); s = fma(th.q[3][cc], 1. / 30., s);
+                                s = fma(th.q[2][cc], 1. / 20., s); s = fma(th.q[1][cc], 1. / 12., s); s = fma(th.q[0][cc], 1. / 6., s);
                                 s = fma(th.a0[cc], 0.5, s);
                                 th.csx[cc] += fma(s, dt2, th.v0[cc] * dt_done);
                                 th.x0[cc] = x + th.csx[cc];
@@ -606,9 +631,9 @@ RV_D void var_run_items(Exec& ex, const VarArgs& a, const VarLayout& L, double* 
                             }
                             {
                                 const double v = th.v0[cc];
-                                double s = th.b[6][cc] * (1. / 8.);
-                                s = fma(th.b[5][cc], 1. / 7., s); s = fma(th.b[4][cc], 1. / 6., s); s = fma(th.b[3][cc], 1. / 5., s);
-                                s = fma(th.b[2][cc], 1. / 4., s); s = fma(th.b[1][cc], 1. / 3., s); s = fma(th.b[0][cc], 1. / 2., s);
+                                double s = th.q[6][cc] * (1. / 8.);
+                                s = fma(th.q[5][cc], 1. / 7., s); s = fma(th.q[4][cc], 1. / 6., s); s = fma(th.q[3][cc], 1. / 5., s);
+                                s = fma(th.q[2][cc], 1. / 4., s); s = fma(th.q[1][cc], 1. / 3., s); s = fma(th.q[0][cc], 1. / 2., s);
                                 s += th.a0[cc];
                                 th.csv[cc] = fma(s, dt_done, th.csv[cc]);
                                 th.v0[cc] = v + th.csv[cc];
@@ -618,11 +643,11 @@ RV_D void var_run_items(Exec& ex, const VarArgs& a, const VarLayout& L, double* 
 #pragma unroll
                             for (int k = 0; k < 7; k++) {
                                 _e[k] = esm[(k * D + cc) * NT + th.tid];
-                                _b[k] = th.b[k][cc];
+                                _b[k] = th.q[k][cc];
                                 hist[(k * D + cc) * NT + th.tid] = _e[k];
                                 hist[((7 + k) * D + cc) * NT + th.tid] = _b[k];
                             }
-                            var_predict<D>(q, _e, _b, e, th.b, cc);
+                            var_predict<D>(q, _e, _b, e, th.q, cc);
 #pragma unroll
                             for (int k = 0; k < 7; k++) esm[(k * D + cc) * NT + th.tid] = e[k];
                         }
