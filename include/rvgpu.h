@@ -69,7 +69,9 @@ int rv_obs_destroy(rv_obs* obs);
 int rv_model_create(rv_ctx* ctx, int n_planets, const double* fixed, int nvars, const int32_t* free_planet,
                     const int32_t* free_elem, double hill_factor, int dims, rv_model** out);
 int rv_model_destroy(rv_model* model);
-/* options: "dt0" (1e-3), "epsilon" (1e-9), "max_attempts", "hill_factor", "mapping" (0 lane-per-planet, 1 thread-per-walker),
+/* options: "integrator" (0 = IAS15, rebound's default and what the reference runs; 1 = WHFast, fixed step "dt0", each leg
+ *   swept monotonically -- no reference call site, parity unpinned; rv_loglik_d_dd / rv_smala_run refuse it),
+ * "dt0" (1e-3), "epsilon" (1e-9), "max_attempts", "hill_factor", "mapping" (0 lane-per-planet, 1 thread-per-walker),
  * "check_prior" (1; 0 = rv_loglik_d_dd integrates even outside the hard prior, as state.py:290 does),
  * "monotone_backward" (0 = rv_loglik visits obs.tb in its stored order as state.py:91 does; 1 = one sweep from 0 to the
  *   most negative epoch, the order state.py:273 uses: about half the backward steps, logp equal to ~1e-11)            */

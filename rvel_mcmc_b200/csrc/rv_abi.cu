@@ -9,6 +9,7 @@
 #include "rv_loglik.cuh"
 #include "rv_model.h"
 #include "rv_var.cuh"
+#include "rv_whfast.cuh"
 
 struct rv_ctx {
     int device;
@@ -216,6 +217,10 @@ int rv_model_set_option(rv_model* m, const char* key, double value) {
     else if (!strcmp(key, "mapping")) m->mapping = (int)value;
     else if (!strcmp(key, "check_prior")) m->h.check_prior = value != 0.0;
     else if (!strcmp(key, "monotone_backward")) m->h.monotone_backward = value != 0.0;
+    else if (!strcmp(key, "integrator")) {
+        if (value != 0.0 && value != 1.0) return fail(ctx, -21, "rv_model_set_option: integrator must be 0 (IAS15) or 1 (WHFast)");
+        m->h.integrator = (int)value;
+    }
     else return fail(ctx, -20, "rv_model_set_option: unknown key '%s'", key);
     CU(ctx, cudaSetDevice(ctx->device));
     CU(ctx, cudaMemcpy(m->d, &m->h, sizeof(rv::Model), cudaMemcpyHostToDevice));
@@ -227,6 +232,17 @@ static int loglik_dev_impl(rv_ctx* ctx, const rv_model* model, const rv_obs* obs
     if (W == 0) return 0;
     if (int rc = ensure(ctx, &ctx->d_part, &ctx->cap_part, (size_t)(2 * W))) return rc;
     if (int rc = ensure(ctx, &ctx->d_pstat, &ctx->cap_pstat, (size_t)(2 * W))) return rc;
+    if (model->h.integrator == 1) {
+        rv::WhArgs wa;
+        memset(&wa, 0, sizeof wa);
+        wa.model = model->d; wa.theta = d_theta; wa.W = W;
+        wa.ot = obs->d_t; wa.orv = obs->d_rv; wa.oerr = obs->d_err; wa.nf = obs->nf; wa.nb = obs->nb;
+        wa.part_chi2 = ctx->d_part; wa.part_status = ctx->d_pstat;
+        wa.work_counters = ctx->count_work ? ctx->d_work : nullptr;
+        CU(ctx, rv::launch_whfast(wa, model->h.P, model->h.D, ctx->num_sms, s));
+        CU(ctx, rv::launch_finalize(ctx->d_part, ctx->d_pstat, W, obs->npoints, d_logp, d_status, ctx->d_item_counter, s));
+        return 0;
+    }
     rv::LoglikArgs a;
     memset(&a, 0, sizeof a);
     a.model = model->d; a.theta = d_theta; a.W = W;
@@ -285,6 +301,18 @@ int rv_rv_curve(rv_ctx* ctx, const rv_model* model, const double* theta, int64_t
         CU(ctx, cudaMemcpyAsync(ctx->d_theta, theta, (size_t)W * model->h.nvars * sizeof(double), cudaMemcpyHostToDevice, s));
     if (nt) CU(ctx, cudaMemcpyAsync(ctx->d_times, times, (size_t)nt * sizeof(double), cudaMemcpyHostToDevice, s));
     CU(ctx, cudaMemsetAsync(ctx->d_rv, 0, (size_t)W * (size_t)(nt > 0 ? nt : 1) * sizeof(double), s));
+    if (model->h.integrator == 1) {
+        rv::WhArgs wa;
+        memset(&wa, 0, sizeof wa);
+        wa.model = model->d; wa.theta = ctx->d_theta; wa.W = W;
+        wa.times = ctx->d_times; wa.nt = nt; wa.rv_out = ctx->d_rv; wa.part_status = ctx->d_pstat;
+        wa.work_counters = ctx->count_work ? ctx->d_work : nullptr;
+        CU(ctx, rv::launch_whfast(wa, model->h.P, model->h.D, ctx->num_sms, s));
+        if (nt) CU(ctx, cudaMemcpyAsync(rv, ctx->d_rv, (size_t)W * nt * sizeof(double), cudaMemcpyDeviceToHost, s));
+        CU(ctx, cudaMemcpyAsync(status, ctx->d_pstat, (size_t)W * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        CU(ctx, cudaStreamSynchronize(s));
+        return 0;
+    }
     rv::LoglikArgs a;
     memset(&a, 0, sizeof a);
     a.model = model->d; a.theta = ctx->d_theta; a.W = W;
@@ -308,6 +336,8 @@ static int var_dev_impl(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, c
                         double* d_logp, double* d_grad, double* d_hess, int32_t* d_status, cudaStream_t s) {
     if (W == 0) return 0;
     const int nv = model->h.nvars;
+    if (model->h.integrator != 0)
+        return fail(ctx, -31, "the variational (gradient + Hessian) path integrates with IAS15 only; set integrator = 0");
     if (rv::var_threads_needed(model->h.P, nv) > 448)
         return fail(ctx, -30, "variational kernel: %d planets x %d free parameters need %d (set, planet) threads; the limit is 448",
                     model->h.P, nv, rv::var_threads_needed(model->h.P, nv));

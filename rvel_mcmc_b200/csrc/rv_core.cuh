@@ -51,6 +51,7 @@ struct Model {
     double m_star;          // 1.0 (state.py:38)
     int max_attempts;       // safety bound on IAS15 step attempts per leg
     int check_prior;        // variational entry point: test priorHard first (1, default) or integrate regardless (0)
+    int integrator;         // 0 = IAS15 (rebound's default, what the reference runs); 1 = WHFast with fixed step dt0
     int monotone_backward;  // plain path: 0 (default) visit obs.tb in stored (ascending) order as state.py:91 does --
                             // first hop to the most negative epoch, then forward; 1 = sweep 0 -> most negative once
                             // (the order state.py:273 uses), half the backward steps, logp equal to ~1e-11

@@ -14,6 +14,9 @@ int var_threads_needed(int P, int nv);
 cudaError_t launch_var(const VarArgs& a, int P, int D, int nv, int num_sms, cudaStream_t stream);
 cudaError_t launch_var_finalize(const double* part, const int* pstat, long long W, int nv, double* logp, double* grad,
                                 double* hess, int* status, unsigned long long* item_counter, cudaStream_t stream);
+// optional WHFast variant (rv_whfast_kernels.cu)
+struct WhArgs;
+cudaError_t launch_whfast(const WhArgs& a, int P, int D, int num_sms, cudaStream_t stream);
 // samplers (rv_samplers.cu)
 cudaError_t launch_mh_propose(const double* theta, const double* scales, double step_size, int nvars, long long W,
                               unsigned long long seed, unsigned long long first_id, unsigned step, double* prop,

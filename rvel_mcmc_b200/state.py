@@ -27,6 +27,10 @@ def _py2_order(planet):
 
 class State(object):
     verbose_prior = False    # the reference prints on every prior rejection (state.py:302-313)
+    # Not in the reference (which always runs rebound's default IAS15): "whfast" selects the optional fixed-step
+    # variant with step `dt` (what `sim.integrator = "whfast"; sim.dt = dt` would be in setup_sim).
+    integrator = "ias15"
+    dt = 0.001
 
     def __init__(self, planets, ignore_vars=[], ignore_params=None):
         for planet in planets:            # re-key in place so iteration order matches the reference's
@@ -91,7 +95,8 @@ class State(object):
         fixed_key = fixed.copy()
         for p, e in zip(fp, fe):
             fixed_key[p, e] = 0.0
-        key = (tuple(fp), tuple(fe), fixed_key.tobytes(), float(hf))
+        whfast = {"ias15": 0, "whfast": 1}[self.integrator]
+        key = (tuple(fp), tuple(fe), fixed_key.tobytes(), float(hf), whfast, float(self.dt))
         m = ctx._models.get(key)
         if m is None:
             if len(ctx._models) > 64:
@@ -99,6 +104,10 @@ class State(object):
                     old.close()
                 ctx._models.clear()
             m = _abi.ModelHandle(ctx, fixed, fp, fe, hf)
+            if whfast or self.dt != 0.001:
+                m.set_option("dt0", self.dt)
+            if whfast:
+                m.set_option("integrator", 1)
             ctx._models[key] = m
         return m
 
@@ -223,8 +232,11 @@ class State(object):
 
     def deepcopy(self):
         # NB like the reference (state.py:212-213) the copy is a fresh State: hillRadiusFactor is back to 1.
-        return State(copy.deepcopy(self.planets), copy.deepcopy(self.ignore_vars),
-                     ignore_params=copy.deepcopy(self.ignore_params))
+        c = State(copy.deepcopy(self.planets), copy.deepcopy(self.ignore_vars),
+                  ignore_params=copy.deepcopy(self.ignore_params))
+        if self.integrator != "ias15":
+            c.integrator, c.dt = self.integrator, self.dt
+        return c
 
     def var_pindex_vname(self, vindex):
         vi = 0

@@ -204,3 +204,57 @@ def mirror_loglik_d_dd(fixed, fp, fe, hill, obs, theta, dims=0):
                                      vp(theta), C.c_longlong(W), vp(logp), vp(grad), vp(hess), vp(status), cnt)
     assert rc == 0, rc
     return logp, grad, hess, status, list(cnt)
+
+
+def orc_whfast_rv(E, hill, dt0, times):
+    E = np.ascontiguousarray(E, dtype=np.float64)
+    times = np.ascontiguousarray(times, dtype=np.float64)
+    rv = np.zeros(len(times))
+    cnt = (C.c_long * 3)()
+    st = oracle().orc_whfast_get_rv(E.shape[0], vp(E), C.c_double(hill), C.c_double(dt0), vp(times), len(times), vp(rv), cnt)
+    return st, rv, int(cnt[1])
+
+
+def orc_whfast_logp_batch(fixed, fp, fe, hill, dt0, obs, theta, nthreads=8):
+    fixed = np.ascontiguousarray(fixed, dtype=np.float64)
+    theta = np.ascontiguousarray(theta, dtype=np.float64)
+    fp = np.ascontiguousarray(fp, dtype=np.int32)
+    fe = np.ascontiguousarray(fe, dtype=np.int32)
+    W = theta.shape[0]
+    logp = np.zeros(W)
+    status = np.zeros(W, dtype=np.int32)
+    cnt = (C.c_long * 3)()
+    oracle().orc_whfast_logp_batch(fixed.shape[0], vp(fixed), len(fp), vp(fp), vp(fe), C.c_double(hill), C.c_double(dt0),
+                                   vp(obs.tf), vp(obs.rvf), vp(obs.errorf), len(obs.tf),
+                                   vp(obs.tb), vp(obs.rvb), vp(obs.errorb), len(obs.tb), C.c_double(obs.Npoints),
+                                   vp(theta), C.c_long(W), vp(logp), vp(status), cnt, nthreads)
+    return logp, status, list(cnt)
+
+
+def mirror_whfast(fixed, fp, fe, hill, dt0, obs, theta, dims=0, times=None):
+    fixed = np.ascontiguousarray(fixed, dtype=np.float64)
+    theta = np.ascontiguousarray(theta, dtype=np.float64)
+    fp = np.ascontiguousarray(fp, dtype=np.int32)
+    fe = np.ascontiguousarray(fe, dtype=np.int32)
+    W = theta.shape[0]
+    logp = np.zeros(W)
+    status = np.zeros(W, dtype=np.int32)
+    cnt = (C.c_ulonglong * 2)()
+    rv = None
+    nt = 0
+    if times is not None:
+        times = np.ascontiguousarray(times, dtype=np.float64)
+        nt = len(times)
+        rv = np.zeros((W, nt))
+    if obs is None:
+        obs = Obs()
+        obs.tf = obs.tb = obs.rvf = obs.rvb = obs.errorf = obs.errorb = np.zeros(0)
+        obs.Npoints = 1
+    rc = mirror().mirror_whfast(fixed.shape[0], vp(fixed), len(fp), vp(fp), vp(fe), C.c_double(hill), dims, C.c_double(dt0),
+                                vp(obs.tf), vp(obs.rvf), vp(obs.errorf), len(obs.tf),
+                                vp(obs.tb), vp(obs.rvb), vp(obs.errorb), len(obs.tb), C.c_double(obs.Npoints),
+                                vp(theta), C.c_longlong(W), vp(logp), vp(status), vp(times), nt, vp(rv), cnt)
+    assert rc == 0, rc
+    if times is not None:
+        return rv, status, list(cnt)
+    return logp, status, list(cnt)

@@ -33,3 +33,17 @@ for mp in [int(x) for x in sys.argv[1:]] or [0]:
     lp = logp.cpu().numpy()
     if ref is None: ref = lp.copy()
     print("mapping %2d: %.2f ms  %.3f Mevals/s  max|dlogp vs first|=%.2e" % (mp, best, W / best / 1e3, np.abs(lp - ref).max()))
+
+# optional WHFast variant, dt = P_inner/20 (BASELINE configs[4])
+m.set_option("mapping", 0)
+for dt_div in (20, 50):
+    m.set_option("dt0", 2 * np.pi * 0.65773033 ** 1.5 / dt_div); m.set_option("integrator", 1)
+    m.loglik_dev(oh, theta.data_ptr(), W, logp.data_ptr(), st.data_ptr(), s); torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); m.loglik_dev(oh, theta.data_ptr(), W, logp.data_ptr(), st.data_ptr(), s); e1.record()
+        torch.cuda.synchronize(); best = min(best, e0.elapsed_time(e1))
+    lp = logp.cpu().numpy()
+    print("WHFast dt=P_inner/%d: %.2f ms  %.3f Mevals/s  max|dlogp vs IAS15|=%.2e" % (dt_div, best, W / best / 1e3, np.abs(lp - ref).max() if ref is not None else -1))
+m.set_option("integrator", 0); m.set_option("dt0", 1e-3)
