@@ -143,6 +143,16 @@ int rv_smala_run(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, double* 
                  double alpha, uint64_t seed, uint64_t first_chain_id, uint32_t first_step, int nsteps, int thin, int64_t W,
                  double* chain, double* chain_logp, uint64_t* n_accept, uint8_t* accepted, int32_t* status);
 
+/* ---- Alsmala (mcmc.py:191-234) driven by run_alsmala's schedule (driver.py:171-200) ---------------------------------- */
+/* Iteration i (= first_step + k) is a full SMALA step with probability exp(-bern_a * i / niter_total) (driver.py:181), else
+ * Alsmala.step_mala: proposal and both transition densities from the STALE gradient / Hessian of the last full step
+ * (mcmc.py:195-212), one plain likelihood evaluation.  The schedule draw is one per iteration, shared by all chains.
+ * full_step[nsteps] (optional) records which iterations were full steps.  Other arguments as rv_smala_run.           */
+int rv_alsmala_run(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, double* theta, double* logp, double eps,
+                   double alpha, double bern_a, int64_t niter_total, uint64_t seed, uint64_t first_chain_id,
+                   uint32_t first_step, int nsteps, int thin, int64_t W, double* chain, double* chain_logp,
+                   uint64_t* n_accept, uint8_t* accepted, int32_t* status, uint8_t* full_step);
+
 /* ---- work accounting: force evaluations and IAS15 step attempts since the last reset ----------- */
 int rv_work_counters(rv_ctx* ctx, uint64_t out[2], int reset);
 int rv_count_work(rv_ctx* ctx, int enable);     /* off by default (atomics per item when on)       */

@@ -79,3 +79,45 @@ def smala_chain(lib, evaluate, prior_hard, theta0, eps, alpha, seed, chain_id, f
         chain[k] = theta
         accepted[k] = 1 if acc else 0
     return chain, accepted, logp
+
+
+RNG_SCHEDULE = 2
+SCHEDULE_ID = 0xFFFFFFFFFFFFFFFF
+
+
+def alsmala_chain(lib, evaluate, evaluate_plain, prior_hard, theta0, eps, alpha, bern_a, niter_total, seed, chain_id,
+                  first_step, nsteps):
+    """Alsmala (mcmc.py:191-234) under run_alsmala's schedule (driver.py:171-200): iteration i is a full SMALA step with
+    probability exp(-bern_a*i/Niter), else step_mala, whose proposal and BOTH transition densities use the stale gradient /
+    Hessian carried by the state (mcmc.py:195-212) and which evaluates only the plain likelihood (evaluate_plain(theta) ->
+    (status, logp)).  Schedule draw: one per iteration, Philox(seed, SCHEDULE_ID, i, RNG_SCHEDULE), shared by all chains.
+    Returns (chain, accepted, full_step, logp_final)."""
+    theta = np.array(theta0, dtype=float)
+    n = len(theta)
+    st, logp, g, H = evaluate(theta)
+    assert st == 0
+    chain = np.zeros((nsteps, n)); accepted = np.zeros(nsteps, dtype=np.uint8); full = np.zeros(nsteps, dtype=np.uint8)
+    for k in range(nsteps):
+        step = first_step + k
+        r = philox(lib, seed, SCHEDULE_ID, step, RNG_SCHEDULE)
+        do_full = np.exp(-bern_a * step / float(niter_total if niter_total > 0 else nsteps)) > _u53(r[0], r[1])
+        full[k] = 1 if do_full else 0
+        mu, Ginv = proposal_mean_cov(theta, g, H, eps, alpha)
+        new = mu + eps * np.dot(np.linalg.cholesky(Ginv), normals(lib, seed, chain_id, step, n))
+        acc = False
+        if not prior_hard(new):
+            q_ts_t = stats.multivariate_normal.logpdf(new, mean=mu, cov=eps ** 2 * Ginv)
+            if do_full:
+                st2, logp2, g2, H2 = evaluate(new)
+            else:
+                st2, logp2 = evaluate_plain(new)
+                g2, H2 = g, H                                   # prop.logp_d = logp_d; prop.logp_dd = logp_dd (mcmc.py:205-206)
+            if st2 == 0:
+                mu2, Ginv2 = proposal_mean_cov(new, g2, H2, eps, alpha)
+                q_t_ts = stats.multivariate_normal.logpdf(theta, mean=mu2, cov=eps ** 2 * Ginv2)
+                ra = philox(lib, seed, chain_id, step, RNG_ACCEPT)
+                acc = np.exp(logp2 - logp + q_t_ts - q_ts_t) > _u53(ra[0], ra[1])
+        if acc:
+            theta, logp, g, H = new, logp2, g2, H2
+        chain[k] = theta; accepted[k] = 1 if acc else 0
+    return chain, accepted, full, logp

@@ -58,6 +58,9 @@ _SIGNATURES = {
     "rv_smala_run": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double,
                                C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p,
                                C.c_void_p, C.c_void_p, C.c_void_p]),
+    "rv_alsmala_run": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double,
+                                 C.c_double, C.c_int64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, C.c_int, C.c_int64,
+                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "rv_stretch_run": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double,
                                  C.c_uint64, C.c_uint32, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_void_p]),
@@ -290,6 +293,27 @@ class ModelHandle(object):
                                                  _ptr(chain), _ptr(chain_lp), _ptr(nacc), _ptr(acc), _ptr(status)),
                        "rv_smala_run")
         return dict(theta=theta, logp=lp, chain=chain, chain_logp=chain_lp, n_accept=nacc, accepted=acc, status=status)
+
+    def alsmala_run(self, obs, theta, eps, alpha, bern_a, nsteps, niter_total=0, seed=0, first_chain_id=0, first_step=0,
+                    thin=1, record_chain=True, record_accepts=False):
+        """W independent ALSMALA chains (Alsmala + run_alsmala's schedule, mcmc.py:191-234, driver.py:171-200) on the device.
+        Returns smala_run's dict plus full_step[nsteps] (1 where the iteration was a full SMALA step)."""
+        theta = self._theta(theta).copy()
+        W = theta.shape[0]
+        lp = np.zeros(W)
+        rows = nsteps // thin
+        chain = np.zeros((rows, W, self.nvars)) if record_chain else None
+        chain_lp = np.zeros((rows, W)) if record_chain else None
+        nacc = np.zeros(W, dtype=np.uint64)
+        acc = np.zeros((nsteps, W), dtype=np.uint8) if record_accepts else None
+        status = np.zeros(W, dtype=np.int32)
+        full = np.zeros(max(nsteps, 1), dtype=np.uint8)
+        self.ctx.check(self.ctx.lib.rv_alsmala_run(self.ctx.h, self.h, obs.h, _ptr(theta), _ptr(lp), float(eps), float(alpha),
+                                                   float(bern_a), int(niter_total), int(seed), int(first_chain_id),
+                                                   int(first_step), int(nsteps), int(thin), W, _ptr(chain), _ptr(chain_lp),
+                                                   _ptr(nacc), _ptr(acc), _ptr(status), _ptr(full)), "rv_alsmala_run")
+        return dict(theta=theta, logp=lp, chain=chain, chain_logp=chain_lp, n_accept=nacc, accepted=acc, status=status,
+                    full_step=full[:nsteps])
 
     def stretch_run(self, obs, theta, nsteps, a=2.0, seed=0, first_step=0, thin=1, lnp=None, record_chain=True,
                     record_accepts=False):

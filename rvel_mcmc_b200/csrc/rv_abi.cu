@@ -10,6 +10,7 @@
 #include "rv_model.h"
 #include "rv_var.cuh"
 #include "rv_whfast.cuh"
+#include "rv_rng.cuh"
 
 struct rv_ctx {
     int device;
@@ -558,9 +559,12 @@ int rv_stretch_run(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, double
     return 0;
 }
 
-int rv_smala_run(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, double* theta, double* logp, double eps,
-                 double alpha, uint64_t seed, uint64_t first_chain_id, uint32_t first_step, int nsteps, int thin, int64_t W,
-                 double* chain, double* chain_logp, uint64_t* n_accept, uint8_t* accepted, int32_t* status) {
+// SMALA (bern_a < 0) and ALSMALA (bern_a >= 0: step i is a full SMALA step with probability exp(-bern_a*i/niter_total),
+// driver.py:181, else a MALA step on the stale derivatives) share one implementation.
+static int smala_impl(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, double* theta, double* logp, double eps,
+                      double alpha, double bern_a, int64_t niter_total, uint64_t seed, uint64_t first_chain_id,
+                      uint32_t first_step, int nsteps, int thin, int64_t W, double* chain, double* chain_logp,
+                      uint64_t* n_accept, uint8_t* accepted, int32_t* status, uint8_t* full_step) {
     if (!ctx || !model || !obs || !theta || !logp) return fail(ctx, -1, "rv_smala_run: NULL argument");
     if (W <= 0 || nsteps < 0) return fail(ctx, -2, "rv_smala_run: bad size");
     const int nv = model->h.nvars;
@@ -600,13 +604,24 @@ int rv_smala_run(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, double* 
         const unsigned step = first_step + (unsigned)k;
         CU(ctx, rv::launch_smala_propose(ctx->d_theta, ctx->d_grad, ctx->d_hess, ctx->d_status, nv, W, eps, alpha, seed,
                                          first_chain_id, step, ctx->d_prop, ctx->d_qf, ctx->d_geo, ctx->d_lascr, s));
-        if (int rc = var_dev_impl(ctx, model, obs, ctx->d_prop, W, ctx->d_plogp, ctx->d_pgrad, ctx->d_phess, ctx->d_pstatus, s)) return rc;
+        bool mala = false;
+        if (bern_a >= 0.0) {       // one schedule draw per iteration, shared by all chains (driver.py:181)
+            const rv::U4 r = rv::philox4x32_10(seed, ~0ull, step, rv::RNG_SCHEDULE);
+            const double total = niter_total > 0 ? (double)niter_total : (double)nsteps;
+            mala = !(exp(-bern_a * (double)step / total) > rv::u53(r.x, r.y));
+        }
+        if (full_step) full_step[k] = mala ? 0 : 1;
+        if (mala) {
+            if (int rc = loglik_dev_impl(ctx, model, obs, ctx->d_prop, W, ctx->d_plogp, ctx->d_pstatus, s)) return rc;
+        } else {
+            if (int rc = var_dev_impl(ctx, model, obs, ctx->d_prop, W, ctx->d_plogp, ctx->d_pgrad, ctx->d_phess, ctx->d_pstatus, s)) return rc;
+        }
         const bool rec = rows && ((k + 1) % thin == 0);
         CU(ctx, rv::launch_smala_accept(ctx->d_theta, ctx->d_logp, ctx->d_grad, ctx->d_hess, ctx->d_prop, ctx->d_plogp,
                                         ctx->d_pgrad, ctx->d_phess, ctx->d_pstatus, ctx->d_geo, ctx->d_qf, nv, W, eps, alpha,
                                         seed, first_chain_id, step, ctx->d_nacc, accepted ? ctx->d_acc + (size_t)k * W : nullptr,
                                         ctx->d_flag, rec ? ctx->d_chain + (size_t)row * W * nv : nullptr,
-                                        rec ? ctx->d_chainlp + (size_t)row * W : nullptr, ctx->d_lascr, s));
+                                        rec ? ctx->d_chainlp + (size_t)row * W : nullptr, ctx->d_lascr, mala ? 1 : 0, s));
         if (rec) row++;
     }
     CU(ctx, cudaMemcpyAsync(theta, ctx->d_theta, (size_t)W * nv * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -620,6 +635,22 @@ int rv_smala_run(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, double* 
     if (status) CU(ctx, cudaMemcpyAsync(status, ctx->d_flag, (size_t)W * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     CU(ctx, cudaStreamSynchronize(s));
     return 0;
+}
+
+int rv_smala_run(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, double* theta, double* logp, double eps,
+                 double alpha, uint64_t seed, uint64_t first_chain_id, uint32_t first_step, int nsteps, int thin, int64_t W,
+                 double* chain, double* chain_logp, uint64_t* n_accept, uint8_t* accepted, int32_t* status) {
+    return smala_impl(ctx, model, obs, theta, logp, eps, alpha, -1.0, 0, seed, first_chain_id, first_step, nsteps, thin, W,
+                      chain, chain_logp, n_accept, accepted, status, nullptr);
+}
+
+int rv_alsmala_run(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, double* theta, double* logp, double eps,
+                   double alpha, double bern_a, int64_t niter_total, uint64_t seed, uint64_t first_chain_id,
+                   uint32_t first_step, int nsteps, int thin, int64_t W, double* chain, double* chain_logp,
+                   uint64_t* n_accept, uint8_t* accepted, int32_t* status, uint8_t* full_step) {
+    if (bern_a < 0.0) return fail(ctx, -2, "rv_alsmala_run: bern_a must be >= 0");
+    return smala_impl(ctx, model, obs, theta, logp, eps, alpha, bern_a, niter_total, seed, first_chain_id, first_step, nsteps,
+                      thin, W, chain, chain_logp, n_accept, accepted, status, full_step);
 }
 
 int rv_count_work(rv_ctx* ctx, int enable) {

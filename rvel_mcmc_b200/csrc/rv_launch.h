@@ -40,6 +40,6 @@ cudaError_t launch_smala_accept(double* theta, double* logp, double* grad, doubl
                                 const int* geo_status, const double* q_fwd, int n, long long W, double eps, double alpha,
                                 unsigned long long seed, unsigned long long first_id, unsigned step,
                                 unsigned long long* n_accept, unsigned char* accepted, int* flag, double* chain_row,
-                                double* chain_logp_row, double* scratch, cudaStream_t s);
+                                double* chain_logp_row, double* scratch, int mala, cudaStream_t s);
 cudaError_t launch_mask_logp(double* logp, const int* status, long long W, cudaStream_t s);
 }  // namespace rv

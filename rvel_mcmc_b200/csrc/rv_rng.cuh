@@ -33,7 +33,7 @@ RV_HD double u53(uint32_t hi, uint32_t lo) {
 }
 
 // stream ids
-enum : uint32_t { RNG_ACCEPT = 1u, RNG_STRETCH_Z = 0x10u, RNG_STRETCH_J = 0x20u, RNG_NORMAL = 0x100u };
+enum : uint32_t { RNG_ACCEPT = 1u, RNG_SCHEDULE = 2u, RNG_STRETCH_Z = 0x10u, RNG_STRETCH_J = 0x20u, RNG_NORMAL = 0x100u };
 
 // two standard normals (Box-Muller) for the pair index j of a walker at a step
 RV_HD void normal_pair(uint64_t seed, uint64_t id, uint32_t step, uint32_t j, double& z0, double& z1) {

@@ -30,16 +30,21 @@ __global__ void smala_accept_kernel(double* __restrict__ theta, double* __restri
                                     unsigned long long first_id, unsigned step, unsigned long long* __restrict__ n_accept,
                                     unsigned char* __restrict__ accepted, int* __restrict__ flag,
                                     double* __restrict__ chain_row, double* __restrict__ chain_logp_row,
-                                    double* __restrict__ scratch) {
+                                    double* __restrict__ scratch, int mala) {
     const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= W) return;
-    const bool acc = smala_accept_one(n, theta + w * n, logp[w], prop + w * n, p_logp[w], p_grad + w * n,
-                                      p_hess + (size_t)w * n * n, p_status[w], geo_status[w], q_fwd[w], eps, alpha, seed,
-                                      first_id + (unsigned long long)w, step, flag ? flag + w : nullptr,
-                                      scratch + (size_t)w * 5 * n * n) != 0;
+    // mala: the proposal carries the current state's (stale) derivatives (mcmc.py:205-206)
+    const double* pg = mala ? grad + w * n : p_grad + w * n;
+    const double* ph = mala ? hess + (size_t)w * n * n : p_hess + (size_t)w * n * n;
+    const bool acc = smala_accept_one(n, theta + w * n, logp[w], prop + w * n, p_logp[w], pg, ph, p_status[w],
+                                      geo_status[w], q_fwd[w], eps, alpha, seed, first_id + (unsigned long long)w, step,
+                                      flag ? flag + w : nullptr, scratch + (size_t)w * 5 * n * n) != 0;
     if (acc) {
-        for (int i = 0; i < n; i++) { theta[w * n + i] = prop[w * n + i]; grad[w * n + i] = p_grad[w * n + i]; }
-        for (int i = 0; i < n * n; i++) hess[(size_t)w * n * n + i] = p_hess[(size_t)w * n * n + i];
+        for (int i = 0; i < n; i++) theta[w * n + i] = prop[w * n + i];
+        if (!mala) {
+            for (int i = 0; i < n; i++) grad[w * n + i] = p_grad[w * n + i];
+            for (int i = 0; i < n * n; i++) hess[(size_t)w * n * n + i] = p_hess[(size_t)w * n * n + i];
+        }
         logp[w] = p_logp[w];
         if (n_accept) n_accept[w] += 1ull;
     }
@@ -64,10 +69,10 @@ cudaError_t launch_smala_accept(double* theta, double* logp, double* grad, doubl
                                 const int* geo_status, const double* q_fwd, int n, long long W, double eps, double alpha,
                                 unsigned long long seed, unsigned long long first_id, unsigned step,
                                 unsigned long long* n_accept, unsigned char* accepted, int* flag, double* chain_row,
-                                double* chain_logp_row, double* scratch, cudaStream_t s) {
+                                double* chain_logp_row, double* scratch, int mala, cudaStream_t s) {
     smala_accept_kernel<<<nblk(W, 64), 64, 0, s>>>(theta, logp, grad, hess, prop, p_logp, p_grad, p_hess, p_status,
                                                    geo_status, q_fwd, n, W, eps, alpha, seed, first_id, step, n_accept,
-                                                   accepted, flag, chain_row, chain_logp_row, scratch);
+                                                   accepted, flag, chain_row, chain_logp_row, scratch, mala);
     return cudaGetLastError();
 }
 

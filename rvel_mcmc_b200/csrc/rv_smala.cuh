@@ -141,6 +141,8 @@ RV_HD int smala_propose_one(int n, const double* __restrict__ th, const double* 
 }
 
 // One chain's accept test.  Returns 1 accept, 0 reject; *flag = ST_NOT_SPD when a metric could not be built.
+// For an ALSMALA "MALA" step (Alsmala.step_mala, mcmc.py:201-234) pass the CURRENT state's stale gradient and Hessian as
+// p_grad / p_hess: the reference copies them onto the proposal (mcmc.py:205-206), so both transition densities use them.
 RV_HD int smala_accept_one(int n, const double* __restrict__ th, double logp, const double* __restrict__ prop, double p_logp,
                            const double* __restrict__ p_grad, const double* __restrict__ p_hess, int p_status,
                            int geo_status, double q_fwd, double eps, double alpha, uint64_t seed, uint64_t id,

@@ -114,6 +114,73 @@ def run_alsmala(label, Niter, true_state, obs, eps, alpha, bern_a, bern_b, print
     return _single_chain(alsmala, label, Niter, true_state, obs, printing_every, stepper)
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# Fused device drivers: the same bundles as run_mh / run_emcee / run_smala / run_alsmala, but the whole propose --
+# evaluate -- accept loop of `nchains` chains (or one ensemble) runs on the GPU in ONE library call
+# (rv_mh_run / rv_stretch_run / rv_smala_run / rv_alsmala_run) instead of one Python iteration per step.  Chains are laid
+# out walker-major like run_emcee's (driver.py:108-112), so ac_times / efficacy / calc_kstatistic apply unchanged.
+# Random numbers are the library's counter-based streams (seed), not numpy's global state.
+
+def _bundle_from_device(sampler_name, r, lp_key, true_state, obs, Niter, nchains, label, t0):
+    chain, chain_lp = r["chain"], r[lp_key]                      # [steps][W][nvars], [steps][W]
+    flat = np.concatenate([chain[:, w, :] for w in range(nchains)], axis=0)
+    flat_lp = np.concatenate([chain_lp[:, w] for w in range(nchains)])
+    bundle = McmcBundle(sampler_name, flat, flat_lp, [t0, datetime.utcnow()], obs, Niter, true_state, is_emcee=True,
+                        Nwalkers=nchains)
+    bundle.device_result = r
+    return bundle, _run_id(true_state, label)
+
+
+def _scale_vector(state, scal):
+    return np.array([scal[k] for k in state.get_rawkeys()], dtype=np.float64)
+
+
+def run_mh_gpu(label, Niter, true_state, obs, scal, step, nchains=1, seed=0):
+    """`nchains` independent MH chains of Niter steps each (Mh.step semantics, mcmc.py:107-121), all started at true_state."""
+    from . import _abi
+    ctx = _abi.default_context()
+    t0 = datetime.utcnow()
+    r = true_state._model(ctx).mh_run(obs._handle(ctx), np.tile(true_state.get_params(), (nchains, 1)),
+                                      _scale_vector(true_state, scal), step, Niter, seed=seed)
+    print("Acceptance rate: %.3f%%" % (100. * r["n_accept"].mean() / max(Niter, 1)))
+    return _bundle_from_device("mh", r, "chain_logp", true_state, obs, Niter * nchains, nchains, label, t0)
+
+
+def run_emcee_gpu(label, Niter, true_state, obs, Nwalkers, scal, seed=0):
+    """One affine-stretch ensemble of Nwalkers (Ensemble + run_emcee, mcmc.py:40-75, driver.py:86-120): Niter/Nwalkers
+    ensemble steps from the reference's start ball theta + 1e-3*scales*N(0,1) (mcmc.py:49-51, numpy RNG as there)."""
+    from . import _abi
+    ctx = _abi.default_context()
+    t0 = datetime.utcnow()
+    sc = _scale_vector(true_state, scal)
+    start = np.array([true_state.get_params() + 1e-3 * sc * np.random.normal(size=true_state.Nvars) for _ in range(Nwalkers)])
+    nsteps = int(Niter / Nwalkers)
+    r = true_state._model(ctx).stretch_run(obs._handle(ctx), start, nsteps, seed=seed)
+    return _bundle_from_device("emcee", r, "chain_lnp", true_state, obs, Niter, Nwalkers, label, t0)
+
+
+def run_smala_gpu(label, Niter, true_state, obs, eps, alpha, nchains=1, seed=0):
+    """`nchains` independent SMALA chains (Smala.step, mcmc.py:167-187)."""
+    from . import _abi
+    ctx = _abi.default_context()
+    t0 = datetime.utcnow()
+    r = true_state._model(ctx).smala_run(obs._handle(ctx), np.tile(true_state.get_params(), (nchains, 1)), eps, alpha,
+                                         Niter, seed=seed)
+    print("Acceptance rate: %.3f%%" % (100. * r["n_accept"].mean() / max(Niter, 1)))
+    return _bundle_from_device("smala", r, "chain_logp", true_state, obs, Niter * nchains, nchains, label, t0)
+
+
+def run_alsmala_gpu(label, Niter, true_state, obs, eps, alpha, bern_a, bern_b=None, nchains=1, seed=0):
+    """`nchains` ALSMALA chains under run_alsmala's schedule exp(-bern_a*i/Niter) (driver.py:171-200; bern_b is unused there)."""
+    from . import _abi
+    ctx = _abi.default_context()
+    t0 = datetime.utcnow()
+    r = true_state._model(ctx).alsmala_run(obs._handle(ctx), np.tile(true_state.get_params(), (nchains, 1)), eps, alpha,
+                                           bern_a, Niter, niter_total=Niter, seed=seed)
+    print("Acceptance rate: %.3f%%" % (100. * r["n_accept"].mean() / max(Niter, 1)))
+    return _bundle_from_device("alsmala", r, "chain_logp", true_state, obs, Niter * nchains, nchains, label, t0)
+
+
 def create_obs(state, npoint, err, errVar, t):
     return observations.FakeObservation(state, Npoints=npoint, error=err, errorVar=errVar, tmax=t)
 

@@ -158,3 +158,28 @@ def test_two_gpu_sharded_samplers_equal_single_gpu():
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert '"stretch_equal_single_gpu": true' in r.stdout and '"mh_shard_equal_single_gpu": true' in r.stdout
+
+
+def test_fused_device_drivers_agree_with_each_other():
+    """driver.run_*_gpu: whole sampling loops in one library call; the reference's cross-sampler KS check (driver.py:416-425)."""
+    from rvel_mcmc_b200 import observations, state, driver
+    np.random.seed(200000)
+    true_state = state.State([{"a": 0.2275, "h": 0., "k": 0., "m": 0.001965}], ignore_vars=["m"])
+    obs = observations.FakeObservation(true_state, Npoints=70, error=3.5e-4, errorVar=9e-5, tmax=1.37)   # (Ex)Full Test notebook
+    scal = {'a': 3e-4, 'h': 0.01, 'k': 0.01}
+    bm, _ = driver.run_mh_gpu("t", 1200, true_state, obs, scal, 5, nchains=64, seed=1)
+    be, _ = driver.run_emcee_gpu("t", 64 * 600, true_state, obs, 64, scal, seed=2)
+    bs, _ = driver.run_smala_gpu("t", 300, true_state, obs, 1.2, 0.14, nchains=64, seed=3)
+    ba, _ = driver.run_alsmala_gpu("t", 300, true_state, obs, 1.2, 0.14, 3.0, nchains=64, seed=4)
+    assert bm.mcmc_chain.shape == (64 * 1200, 3) and be.mcmc_chain.shape == (64 * 600, 3) and bs.mcmc_chain.shape == (64 * 300, 3)
+
+    def trimmed(b, per, burn):
+        c = b.mcmc_chain.reshape(64, per, 3)[:, burn:, :]
+        return c.reshape(-1, 3)
+    cm, ce, cs, ca = trimmed(bm, 1200, 200), trimmed(be, 600, 150), trimmed(bs, 300, 50), trimmed(ba, 300, 50)
+    for name, other in (("emcee", ce), ("smala", cs), ("alsmala", ca)):
+        ks = driver.calc_kstatistic(cm[::7], other[::3])
+        assert max(ks) < 0.06, (name, ks)                                        # notebook: D = 0.014-0.050 between samplers
+    assert driver.ac_times(bs).max() <= 3                                       # SMALA AC 1/1/1 in the notebook
+    # the truth is recovered
+    assert abs(cs[:, 0].mean() - 0.2275) < 4 * cs[:, 0].std()

@@ -105,3 +105,44 @@ def test_smala_posterior_agrees_with_mh(ctx):
         mcse = np.sqrt(a[:, i].var() / max(ne_a, 10) + b[:, i].var() / max(ne_b, 10))
         assert abs(a[:, i].mean() - b[:, i].mean()) < 5 * mcse + 1e-12, i
         assert abs(a[:, i].std() / b[:, i].std() - 1.0) < 0.15
+
+
+def test_alsmala_identical_decisions_and_schedule(ctx):
+    # Alsmala + run_alsmala's schedule (mcmc.py:191-234, driver.py:171-200): full steps early, cheap MALA steps later
+    obs, E, fp, fe, center = _small_problem()
+    oh, m = _handles(ctx, obs, E, fp, fe, 1.0)
+    W, nsteps, eps, alpha, bern_a = 8, 400, 1.2, 0.14, 3.0
+    theta0 = T.gaussian_ball(center, [3e-4, 0.01, 0.01], W, 4, width=0.3)
+    r = m.alsmala_run(oh, theta0, eps, alpha, bern_a, nsteps, seed=41, record_accepts=True)
+
+    def evaluate(theta):
+        lo, go, ho, so, _ = T.orc_logp_d_dd_batch(E, fp, fe, 1.0, obs, np.atleast_2d(theta), nthreads=1)
+        return int(so[0]), float(lo[0]), go[0], ho[0]
+
+    def evaluate_plain(theta):
+        lo, so, _ = T.orc_logp_batch(E, fp, fe, 1.0, obs, np.atleast_2d(theta), nthreads=1)
+        return int(so[0]), float(lo[0])
+
+    def prior(theta):
+        el = np.ascontiguousarray(E.copy().reshape(-1))
+        for v in range(len(fp)):
+            el[fp[v] * 7 + fe[v]] = theta[v]
+        return bool(T.oracle().orc_prior_hard(1, T.vp(el)))
+
+    def one(w):
+        return S.alsmala_chain(T.oracle(), evaluate, evaluate_plain, prior, theta0[w], eps, alpha, bern_a, 0, 41, w, 0, nsteps)
+
+    with ThreadPoolExecutor(8) as ex:
+        res = list(ex.map(one, range(W)))
+    acc_o = np.stack([x[1] for x in res], axis=1); chain_o = np.stack([x[0] for x in res], axis=1)
+    assert np.array_equal(r["full_step"], res[0][2])
+    assert 0.15 < r["full_step"].mean() < 0.6 and r["full_step"][:20].mean() > r["full_step"][-100:].mean()
+    assert np.array_equal(r["accepted"], acc_o)
+    assert np.abs(r["chain"] - chain_o).max() < 1e-8
+    # same posterior as SMALA (reference's cross-sampler check), far fewer variational evaluations
+    al = m.alsmala_run(oh, np.tile(center, (256, 1)), eps, alpha, bern_a, 600, seed=2, thin=2)
+    sm = m.smala_run(oh, np.tile(center, (256, 1)), eps, alpha, 600, seed=3, thin=2)
+    a = al["chain"][100:].reshape(-1, 3); b = sm["chain"][100:].reshape(-1, 3)
+    for i in range(3):
+        assert abs(a[:, i].mean() - b[:, i].mean()) < 0.1 * b[:, i].std()
+        assert abs(a[:, i].std() / b[:, i].std() - 1.0) < 0.15
