@@ -103,11 +103,11 @@ struct WalkerG : Walker<P, D, PL, VAR> {
         double xp[NC], at[NC], dg6[NC];
 #pragma unroll
         for (int c = 0; c < NC; c++) { xp[c] = x0[c]; at[c] = a0[c]; dg6[c] = 0.0; }
-        double pc_err = 1e300, pc_last = 2.0;
+        Ratio pc_err{1e300, 1.0}, pc_last{2.0, 1.0};
         int it = 0;
         bool iterating = active;
         while (true) {
-            if (iterating && (pc_err < 1e-16 || (it > 2 && pc_last <= pc_err) || it >= 12)) iterating = false;
+            if (iterating && (ratio_lt(pc_err, 1e-16) || (it > 2 && ratio_le(pc_last, pc_err)) || it >= 12)) iterating = false;
             if (!warp_any(iterating)) break;
             if (iterating) { pc_last = pc_err; it++; }
             substep_g<1>(iterating, x0c, xp, at, dg6);
@@ -134,7 +134,7 @@ struct WalkerG : Walker<P, D, PL, VAR> {
             }
             maxdg = grp.template gmax<true>(maxdg);
             maxat = grp.template gmax<true>(maxat);
-            if (iterating) { pc_err = maxdg / maxat; n_force += 7; }
+            if (iterating) { pc_err.num = maxdg; pc_err.den = maxat; n_force += 7; }
         }
         if (active) n_force += 1;
         // b from g, in place (b_k needs g_j for j > k only)
@@ -155,7 +155,7 @@ struct WalkerG : Walker<P, D, PL, VAR> {
             double v2 = 0.0, x2 = 0.0;
 #pragma unroll
             for (int d = 0; d < D; d++) { v2 = fma(v0[pl * D + d], v0[pl * D + d], v2); x2 = fma(xp[pl * D + d], xp[pl * D + d], x2); }
-            const bool keep = !(fabs(v2 * dt * dt / x2) < 1e-16);
+            const bool keep = !(fabs(v2 * dt * dt) < 1e-16 * x2);
 #pragma unroll
             for (int d = 0; d < D; d++) {
                 const double ak = fabs(at[pl * D + d]), b6 = fabs(b[6][pl * D + d]);
@@ -171,7 +171,7 @@ struct WalkerG : Walker<P, D, PL, VAR> {
                 v2 = fma(sv, sv, v2); x2 = fma(sx, sx, x2);
                 sa[d] = fabs(this->template star_of<true>(at, d)); sb[d] = fabs(this->template star_of<true>(b[6], d));
             }
-            const bool keep = star_in_norm && !(fabs(v2 * dt * dt / x2) < 1e-16);
+            const bool keep = star_in_norm && !(fabs(v2 * dt * dt) < 1e-16 * x2);
 #pragma unroll
             for (int d = 0; d < D; d++) {
                 if (keep && is_normal(sa[d]) && sa[d] > maxak) maxak = sa[d];
@@ -185,9 +185,9 @@ struct WalkerG : Walker<P, D, PL, VAR> {
             const double err = maxb6 / maxak;
             const double dt_done = dt;
             double dt_new;
-            if (is_normal(err)) dt_new = pow(epsilon / err, 1.0 / 7.0) * dt_done;
-            else dt_new = dt_done / 0.25;
-            if (fabs(dt_new / dt_done) < 0.25) {
+            if (is_normal(err)) dt_new = inv_root7(err / epsilon) * dt_done;
+            else dt_new = dt_done * 4.0;
+            if (fabs(dt_new) < 0.25 * fabs(dt_done)) {
                 dt = dt_new;
                 if (dt_last_done != 0.0) {
                     const double q = dt / dt_last_done;
@@ -202,7 +202,7 @@ struct WalkerG : Walker<P, D, PL, VAR> {
                     // no history yet: rebound retries with the b it holds (the corrected ones)
                 }
             } else {
-                if (fabs(dt_new / dt_done) > 1.0 && dt_new / dt_done > 4.0) dt_new = dt_done / 0.25;
+                if (fabs(dt_new) > 4.0 * fabs(dt_done)) dt_new = dt_done * 4.0;      // same sign: dt_new/dt_done > 1/safety
                 dt = dt_new;
                 const double dt2 = dt_done * dt_done;
 #pragma unroll

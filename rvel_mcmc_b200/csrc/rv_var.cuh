@@ -517,11 +517,11 @@ RV_D void var_run_items(Exec& ex, const VarArgs& a, const VarLayout& L, double* 
                     }
                 });
                 int buf = cur ^ 1;
-                double pc_err = 1e300, pc_last = 2.0;
+                Ratio pc_err{1e300, 1.0}, pc_last{2.0, 1.0};
                 int it = 0;
                 const double dt = w.dt;
                 while (true) {
-                    if (pc_err < 1e-16 || (it > 2 && pc_last <= pc_err) || it >= 12) break;
+                    if (ratio_lt(pc_err, 1e-16) || (it > 2 && ratio_le(pc_last, pc_err)) || it >= 12) break;
                     pc_last = pc_err;
                     it++;
 #pragma unroll 1
@@ -548,7 +548,7 @@ RV_D void var_run_items(Exec& ex, const VarArgs& a, const VarLayout& L, double* 
                     ex.sync();
                     double maxdg, maxat;
                     ex.read_max(maxdg, maxat);
-                    pc_err = maxdg / maxat;
+                    pc_err.num = maxdg; pc_err.den = maxat;
                     n_force += 7;
                 }
                 n_force += 1;
@@ -571,7 +571,7 @@ RV_D void var_run_items(Exec& ex, const VarArgs& a, const VarLayout& L, double* 
                         double v2 = 0.0, x2 = 0.0;
 #pragma unroll
                         for (int cc = 0; cc < D; cc++) { v2 = fma(th.v0[cc], th.v0[cc], v2); x2 = fma(th.xn[cc], th.xn[cc], x2); }
-                        const bool keep = !(fabs(v2 * dt * dt / x2) < 1e-16);
+                        const bool keep = !(fabs(v2 * dt * dt) < 1e-16 * x2);
 #pragma unroll
                         for (int cc = 0; cc < D; cc++) {
                             const double ak = fabs(th.at[cc]), b6 = fabs(th.q[6][cc]);
@@ -587,10 +587,10 @@ RV_D void var_run_items(Exec& ex, const VarArgs& a, const VarLayout& L, double* 
                 const double err = maxb6 / maxak;
                 const double dt_done = dt;
                 double dt_new;
-                if (is_normal(err)) dt_new = pow(u.epsilon / err, 1.0 / 7.0) * dt_done;
-                else dt_new = dt_done / 0.25;
+                if (is_normal(err)) dt_new = inv_root7(err / u.epsilon) * dt_done;
+                else dt_new = dt_done * 4.0;
                 int result = 0;
-                if (fabs(dt_new / dt_done) < 0.25) {
+                if (fabs(dt_new) < 0.25 * fabs(dt_done)) {
                     w.dt = dt_new;
                     if (w.dt_last_done != 0.0) {
                         const double q = w.dt / w.dt_last_done;
@@ -611,7 +611,7 @@ RV_D void var_run_items(Exec& ex, const VarArgs& a, const VarLayout& L, double* 
                         });
                     }
                 } else {
-                    if (fabs(dt_new / dt_done) > 1.0 && dt_new / dt_done > 4.0) dt_new = dt_done / 0.25;
+                    if (fabs(dt_new) > 4.0 * fabs(dt_done)) dt_new = dt_done * 4.0;
                     w.dt = dt_new;
                     const double dt2 = dt_done * dt_done;
                     const double q = w.dt / dt_done;
