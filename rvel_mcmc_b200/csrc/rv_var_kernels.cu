@@ -116,7 +116,7 @@ cudaError_t launch_var(const VarArgs& a, int P, int D, int nv, int num_sms, cuda
     if (P == 1 && D == 2 && need <= 64) return launch_var_one<1, 2, 64, 4>(a, nv, num_sms, stream);
     if (P == 1 && D == 3 && need <= 64) return launch_var_one<1, 3, 64, 4>(a, nv, num_sms, stream);
     if (P == 2 && D == 2 && need <= 64) return launch_var_one<2, 2, 64, 4>(a, nv, num_sms, stream);
-    if (P == 2 && D == 2 && need <= 160) return launch_var_one<2, 2, 160, 2>(a, nv, num_sms, stream);
+    if (P == 2 && D == 2 && need <= 160) return launch_var_one<2, 2, 160, 3>(a, nv, num_sms, stream);
     if (P == 2 && D == 3 && need <= 256) return launch_var_one<2, 3, 256, 1>(a, nv, num_sms, stream);
     if (P == 3 && D == 2 && need <= 448) return launch_var_one<3, 2, 448, 1>(a, nv, num_sms, stream);
     if (P == 3 && D == 3 && need <= 448) return launch_var_one<3, 3, 448, 1>(a, nv, num_sms, stream);
