@@ -280,9 +280,12 @@ def main():
     achieved = flops_eval * W / (kernel_ms * 1e-3) / 1e12
     peak = ctx.fp64_peak_tflops()
     roofline = {"bound": "fp64_fma_pipe", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": 5.33e6, "traffic_note": "dram bytes per launch, profiles/r01e_ncu_loglik_kernel.txt (algorithmic: %d B)" % (W * 92),
-                "executed": "the kernel executes fewer FP64 instructions than the algorithmic count (implicit star, coplanar, "
-                            "g-only corrector loop): ncu sm__pipe_fp64_cycles_active = 63%% of peak (profiles/r01e_ncu_loglik_kernel.txt)",
+                "traffic": 5.33e6, "traffic_note": "dram bytes per launch, profiles/r01j_ncu_loglik_kernel.txt (algorithmic: %d B)" % (W * 92),
+                "executed_frac": 0.70,
+                "executed_note": "frac uses SURVEY 8(d)'s ALGORITHMIC flop count (rebound's formulation); the kernel executes fewer "
+                                 "FP64 instructions per decision (implicit star, coplanar, g-only corrector loop, no divisions), so frac can "
+                                 "exceed the pipe's real occupancy: ncu sm__pipe_fp64_cycles_active = 70%% of peak "
+                                 "(profiles/r01j_ncu_loglik_kernel.txt)",
                 "note": "achieved = SURVEY 8(d) algorithmic flops (S=%.0f force evals, T=%.0f step attempts per eval, "
                         "432*S+1350*T) / CUDA-event kernel time; peak = dependent-free fma.rn.f64 microbenchmark on this GPU "
                         "(rv_fp64_peak; MEASURED_PEAKS.json has no FP64 entry)" % (S_eval, T_eval)}
