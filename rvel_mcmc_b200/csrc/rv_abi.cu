@@ -155,7 +155,7 @@ int rv_obs_create(rv_ctx* ctx, const double* tf, const double* rvf, const double
                   rv_obs** out) {
     if (!ctx || !out) return fail(ctx, -1, "rv_obs_create: NULL argument");
     if (nf < 0 || nb < 0 || nf + nb == 0) return fail(ctx, -2, "rv_obs_create: empty observation set");
-    if (nf + nb > 8000) return fail(ctx, -3, "rv_obs_create: %d epochs exceed the shared-memory staging limit (8000)", nf + nb);
+    if ((long long)nf + nb > (1 << 24)) return fail(ctx, -3, "rv_obs_create: %lld epochs exceed the limit of 2^24", (long long)nf + nb);
     CU(ctx, cudaSetDevice(ctx->device));
     rv_obs* o = new (std::nothrow) rv_obs();
     if (!o) return fail(ctx, -12, "out of host memory");

@@ -31,16 +31,21 @@ template <int P, int D, int PL, int NT, int MINB, int VAR>
 __global__ void __launch_bounds__(NT, MINB) loglik_kernel(const LoglikArgs a) {
     extern __shared__ double sm[];
     const int nobs = a.nf + a.nb;
-    double* st = sm;
-    double* srv = sm + nobs;
-    double* serr = sm + 2 * nobs;
-    double* hist = sm + 3 * nobs;
-    for (int i = threadIdx.x; i < nobs; i += NT) {
-        st[i] = a.ot[i];
-        srv[i] = a.orv[i];
-        serr[i] = a.oerr[i];
+    // observation epochs / velocities / errors: staged in shared memory when that does not cost occupancy
+    // (launch_one decides), else read from global memory (one read per epoch reached, L1/L2-resident)
+    const double *st = a.ot, *srv = a.orv, *serr = a.oerr;
+    double* hist = sm;
+    if (a.stage_obs) {
+        double* so = sm;
+        for (int i = threadIdx.x; i < nobs; i += NT) {
+            so[i] = a.ot[i];
+            so[nobs + i] = a.orv[i];
+            so[2 * nobs + i] = a.oerr[i];
+        }
+        st = so; srv = so + nobs; serr = so + 2 * nobs;
+        hist = sm + 3 * nobs;
+        __syncthreads();
     }
-    __syncthreads();
     using W = WalkerG<P, D, PL, VAR>;
     W w;
     const int lane = threadIdx.x & 31;
@@ -74,7 +79,12 @@ static cudaError_t launch_one(const LoglikArgs& a, int num_sms, cudaStream_t str
     const int nobs = a.nf + a.nb;
     constexpr int NC = PL * D;
     constexpr int W21 = WalkerG<P, D, PL, VAR>::HIST;
-    const size_t smem = sizeof(double) * ((size_t)3 * nobs + (size_t)W21 * NC * NT);
+    const size_t smem_hist = sizeof(double) * (size_t)W21 * NC * NT;
+    const size_t smem_obs = sizeof(double) * (size_t)3 * nobs;
+    LoglikArgs args = a;
+    // stage the observations only while MINB CTAs still fit in the SM's 227 KB of shared memory
+    args.stage_obs = ((smem_hist + smem_obs + 1024) * MINB <= (size_t)227 * 1024) ? 1 : 0;
+    const size_t smem = smem_hist + (args.stage_obs ? smem_obs : 0);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int occ = 0;
@@ -88,7 +98,7 @@ static cudaError_t launch_one(const LoglikArgs& a, int num_sms, cudaStream_t str
     const long long need = (n_items + groups_per_block - 1) / groups_per_block;
     if (need < blocks) blocks = need;
     if (blocks < 1) blocks = 1;
-    kern<<<(unsigned)blocks, NT, smem, stream>>>(a);
+    kern<<<(unsigned)blocks, NT, smem, stream>>>(args);
     return cudaGetLastError();
 }
 

@@ -19,6 +19,7 @@ struct LoglikArgs {
     const double* orv;
     const double* oerr;
     int nf, nb;
+    int stage_obs;            // set by the launcher: copy the observation arrays into shared memory
     // RV-curve mode (state.py:61-73 get_rv on arbitrary times): one item per walker, no prior test
     const double* times;
     int nt;
