@@ -304,7 +304,7 @@ def main():
     model.set_option("monotone_backward", 0)
 
     cpu_baseline = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:        # a reported baseline: rank 0 at N = 1 only
         cores = os.cpu_count() or 1
         t_probe, _, _, _ = oracle_batch(obs, host_theta[1][:cores * 8].numpy(), cores)      # size the sample: ~15 s of CPU work
         sample = args.cpu_sample or int(min(W, max(cores * 32, 15.0 / max(t_probe, 1e-3) * cores * 8)))
