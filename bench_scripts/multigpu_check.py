@@ -26,6 +26,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--walkers", type=int, default=4096)
     ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--ess-steps", type=int, default=0, help="also run this many recorded ensemble steps and report ESS/s")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -56,6 +57,19 @@ def main():
     if d: dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     out = {"n_gpus": world, "walkers": W, "ensemble_steps": nsteps, "ms": float(ms.item()),
            "stretch_evals_per_s": W * (nsteps + 1) / (float(ms.item()) * 1e-3)}
+    if args.ess_steps:
+        from rvel_mcmc_b200.samplers import ess
+        torch.cuda.synchronize()
+        if d: dist.barrier()
+        t0 = time.perf_counter()
+        rr = stretch_run_sharded(m, oh, theta0, args.ess_steps, seed=78, dist=d, record_chain=True, thin=1)
+        sec = time.perf_counter() - t0
+        if rank == 0:
+            c = rr["chain"][args.ess_steps // 4:, ::max(1, W // 256), :]          # tau from a 256-walker subsample
+            n_eff, tau = ess(c)
+            out["ess"] = {"ensemble_steps": args.ess_steps, "seconds": sec, "tau_int_max": tau,
+                          "ess_per_s": (args.ess_steps - args.ess_steps // 4) * W / max(tau, 1.0) / sec,
+                          "evals_per_s": W * (args.ess_steps + 1) / sec}
     # reference results on one GPU (rank 0 only)
     lo, hi = chain_shard(W, rank, world)
     scales = np.array(T.HD_SCALE_VEC)

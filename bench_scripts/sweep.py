@@ -167,6 +167,19 @@ def main():
             sec = maxsec(e0.elapsed_time(e1) * 1e-3)
             emit({"config": "C5 sweep, HD155358-shape truth, IAS15", "walkers": W, "epochs": nep + 1, "ms": 1e3 * sec,
                   "evals_per_s": W / sec, "ok_fraction": float((stt == 0).float().mean().item())})
+            if W == 10 ** 5 or args.quick:
+                # the optional WHFast variant on the same batch, dt = P_inner/20 (BASELINE configs[4]; parity unpinned)
+                ref = lp.clone()
+                m.set_option("dt0", p_inner / 20.); m.set_option("integrator", 1)
+                m.loglik_dev(oh, th.data_ptr(), min(hi - lo, 1024), lp.data_ptr(), stt.data_ptr(), s); torch.cuda.synchronize()
+                e0.record(); m.loglik_dev(oh, th.data_ptr(), hi - lo, lp.data_ptr(), stt.data_ptr(), s); e1.record()
+                torch.cuda.synchronize()
+                sec = maxsec(e0.elapsed_time(e1) * 1e-3)
+                okb = stt == 0
+                emit({"config": "C5 sweep, HD155358-shape truth, WHFast dt=P_inner/20", "walkers": W, "epochs": nep + 1,
+                      "ms": 1e3 * sec, "evals_per_s": W / sec, "ok_fraction": float(okb.float().mean().item()),
+                      "max_abs_dlogp_vs_ias15": float((lp[okb] - ref[okb]).abs().max().item())})
+                m.set_option("integrator", 0); m.set_option("dt0", 1e-3)
     if world > 1:
         dist.barrier(); dist.destroy_process_group()
 
