@@ -63,6 +63,8 @@ struct VarThread {
     int tid, set, planet, order;   // order: 0 real, 1 first, 2 second, -1 idle
     int sa, sb;                    // parent sets (first-order sets of parameters pa, pb)
     int pa, pb;                    // parameter indices (pa >= pb)
+    int ou, oa, ob;                // element offsets of the own / parent sets in a position buffer (set * P * D)
+    int ma, mb;                    // offsets of the parents' mass-derivative rows (pa * P, pb * P)
     double x0[D], v0[D], a0[D], ha0[D], csx[D], csv[D], x0c[D];
     double q[7][D];                // b coefficients between step attempts, g coefficients inside the predictor-corrector loop
     double xn[D], at[D], dg6[D];   // last predictor position, last force, last change of g6 (= b6)
@@ -88,6 +90,25 @@ RV_HD double rinv1(double r2) {
 #else
     return 1.0 / sqrt(r2);
 #endif
+}
+
+// positions of the P planets of one set from an exchange buffer (16-byte loads when D == 2)
+template <int P, int D>
+RV_D void load_set(const double* __restrict__ Xs, double (&out)[P][D]) {
+#if defined(__CUDA_ARCH__)
+    if constexpr (D == 2) {
+#pragma unroll
+        for (int j = 0; j < P; j++) {
+            const double2 v = *reinterpret_cast<const double2*>(Xs + 2 * j);
+            out[j][0] = v.x; out[j][1] = v.y;
+        }
+        return;
+    }
+#endif
+#pragma unroll
+    for (int j = 0; j < P; j++)
+#pragma unroll
+        for (int d = 0; d < D; d++) out[j][d] = Xs[j * D + d];
 }
 
 // Acceleration (order 0), first variation (order 1) or second variation (order 2) of the thread's planet,
@@ -129,8 +150,8 @@ RV_D void var_force(const VarThread<P, D>& th, const double* __restrict__ X, con
             for (int d = 0; d < D; d++) an[d] = fma(k, dp[d], an[d]);
         }
     } else if (th.order == 1) {
-        const double* XU = X + th.set * P * D;
-        const double* dma = dm + th.pa * P;
+        const double* XU = X + th.ou;
+        const double* dma = dm + th.ma;
         double S[D], SU[D];
 #pragma unroll
         for (int d = 0; d < D; d++) {
@@ -163,22 +184,23 @@ RV_D void var_force(const VarThread<P, D>& th, const double* __restrict__ X, con
             for (int d = 0; d < D; d++) an[d] -= fma(kU, U[d], kd * dd[d]);
         }
     } else {
-        const double* XA = X + th.sa * P * D;
-        const double* XB = X + th.sb * P * D;
-        const double* XU = X + th.set * P * D;
-        const double* dma = dm + th.pa * P;
-        const double* dmb = dm + th.pb * P;
+        double x0[P][D], xa[P][D], xb[P][D], xu[P][D];
+        load_set<P, D>(X, x0);
+        load_set<P, D>(X + th.oa, xa);
+        load_set<P, D>(X + th.ob, xb);
+        load_set<P, D>(X + th.ou, xu);
+        const double* dma = dm + th.ma;
+        const double* dmb = dm + th.mb;
         double S[D], SA[D], SB[D], SU[D];
 #pragma unroll
         for (int d = 0; d < D; d++) {
             S[d] = 0.0; SA[d] = 0.0; SB[d] = 0.0; SU[d] = 0.0;
 #pragma unroll
             for (int j = 0; j < P; j++) {
-                const double x0j = X0[j * D + d], xaj = XA[j * D + d], xbj = XB[j * D + d];
-                S[d] = fma(u.mu[j], x0j, S[d]);
-                SA[d] = fma(u.mu[j], xaj, fma(dma[j], x0j, SA[d]));
-                SB[d] = fma(u.mu[j], xbj, fma(dmb[j], x0j, SB[d]));
-                SU[d] = fma(u.mu[j], XU[j * D + d], fma(dma[j], xbj, fma(dmb[j], xaj, SU[d])));
+                S[d] = fma(u.mu[j], x0[j][d], S[d]);
+                SA[d] = fma(u.mu[j], xa[j][d], fma(dma[j], x0[j][d], SA[d]));
+                SB[d] = fma(u.mu[j], xb[j][d], fma(dmb[j], x0[j][d], SB[d]));
+                SU[d] = fma(u.mu[j], xu[j][d], fma(dma[j], xb[j][d], fma(dmb[j], xa[j][d], SU[d])));
             }
         }
 #pragma unroll
@@ -190,12 +212,17 @@ RV_D void var_force(const VarThread<P, D>& th, const double* __restrict__ X, con
             double r2 = 0.0, da = 0.0, db = 0.0, ab = 0.0, du = 0.0;
 #pragma unroll
             for (int d = 0; d < D; d++) {
+                // own planet's values: p is a runtime index into register arrays of length P -> select
+                double x0p = x0[0][d], xap = xa[0][d], xbp = xb[0][d], xup = xu[0][d];
+#pragma unroll
+                for (int k = 1; k < P; k++) {
+                    x0p = (p == k) ? x0[k][d] : x0p; xap = (p == k) ? xa[k][d] : xap;
+                    xbp = (p == k) ? xb[k][d] : xbp; xup = (p == k) ? xu[k][d] : xup;
+                }
                 if (j < 0) {
-                    dd[d] = X0[p * D + d] + S[d]; A[d] = XA[p * D + d] + SA[d];
-                    B[d] = XB[p * D + d] + SB[d]; U[d] = XU[p * D + d] + SU[d];
+                    dd[d] = x0p + S[d]; A[d] = xap + SA[d]; B[d] = xbp + SB[d]; U[d] = xup + SU[d];
                 } else {
-                    dd[d] = X0[p * D + d] - X0[j * D + d]; A[d] = XA[p * D + d] - XA[j * D + d];
-                    B[d] = XB[p * D + d] - XB[j * D + d]; U[d] = XU[p * D + d] - XU[j * D + d];
+                    dd[d] = x0p - x0[j][d]; A[d] = xap - xa[j][d]; B[d] = xbp - xb[j][d]; U[d] = xup - xu[j][d];
                 }
                 r2 = fma(dd[d], dd[d], r2);
                 da = fma(dd[d], A[d], da);
@@ -263,7 +290,7 @@ RV_D void var_substep_predict(VarThread<P, D>& th, int n, double dt, double* __r
         p1 = fma(c6, th.q[6][c], p1);
         const double inner = fma(dth, p0 + p1, th.v0[c]);
         th.xn[c] = fma(dth, inner, th.x0c[c]);
-        Xw[(th.set * P + th.planet) * D + c] = th.xn[c];
+        Xw[th.ou + th.planet * D + c] = th.xn[c];
     }
 }
 
@@ -352,6 +379,8 @@ RV_D void var_assign(VarThread<P, D>& th, int tid, const VarLayout& L) {
         th.pa = th.pb = th.set == 0 ? 0 : th.set - 1;
         th.sa = th.sb = th.set;
     }
+    th.ou = th.set * P * D; th.oa = th.sa * P * D; th.ob = th.sb * P * D;
+    th.ma = th.pa * P; th.mb = th.pb * P;
 }
 
 // Initial conditions of the thread's (set, planet): the jet of the barycentric state with respect to the

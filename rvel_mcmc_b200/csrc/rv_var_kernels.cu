@@ -50,7 +50,7 @@ struct DevVarExec {
 
 template <int P, int D, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) var_kernel(const VarArgs a, const VarLayout L) {
-    extern __shared__ double sm[];
+    extern __shared__ __align__(16) double sm[];
     VarThread<P, D> th;
     var_assign(th, (int)threadIdx.x, L);
     DevVarExec<P, D> ex{th, sm + L.o_red, 0, NT / 32};
