@@ -119,176 +119,162 @@ class StretchSampler(object):
         return p, lnprob, self.random_state
 
 
+def _scale_vector(state, scales):
+    """Per-parameter scale vector in get_params() order; parameters without an entry keep 1 (mcmc.py:69-75, 98-104)."""
+    return np.array([float(scales.get(k, 1.0)) for k in state.get_rawkeys()], dtype=np.float64)
+
+
+def _collision():
+    print("Collision! {t}".format(t=datetime.utcnow()))
+    return False
+
+
 class Ensemble(Mcmc):
-    """emcee-style affine sampler coupled with the CUDA engine (mcmc.py:40-75)."""
+    """emcee-style affine sampler coupled with the CUDA engine (mcmc.py:40-75): the walkers start in a ball
+    theta + 1e-3*scales*N(0,1) (numpy's global RNG, one normal(size=Nvars) per walker), and each step() is one
+    stretch-move sweep over both half-ensembles, every half evaluated as ONE batched kernel call."""
 
     def __init__(self, initial_state, obs, scales, nwalkers=10, live_dangerously=False):
-        super(Ensemble, self).__init__(initial_state, obs)
+        Mcmc.__init__(self, initial_state, obs)
         self.set_scales(scales)
         self.nwalkers = nwalkers
-        self.states = [self.state.get_params() for i in range(nwalkers)]
-        self.previous_states = [self.state.get_params() for i in range(nwalkers)]
+        centre = self.state.get_params()
+        self.previous_states = [centre.copy() for _ in range(nwalkers)]
+        self.states = [centre + 0.1e-2 * self.scales * np.random.normal(size=self.state.Nvars) for _ in range(nwalkers)]
         self.lnprob = None
         self.totalErrorCount = 0
-        for i, s in enumerate(self.states):
-            shift = 0.1e-2 * self.scales * np.random.normal(size=self.state.Nvars)
-            self.states[i] += shift
         self.sampler = StretchSampler(nwalkers, self.state.Nvars, lnprob_batch, args=[self],
                                       live_dangerously=live_dangerously)
 
     def step(self):
+        """One ensemble sweep; True iff any walker moved (mcmc.py:57-65)."""
+        before = np.asarray(self.states, dtype=np.float64)
         self.previous_states = self.states
-        self.states, self.lnprob, rstate = self.sampler.run_mcmc(self.states, 1, lnprob0=self.lnprob)
-        for i in range(len(self.states)):
-            for j in range(len(self.states[0])):
-                if self.previous_states[i][j] != self.states[i][j]:
-                    return True
-        else:
-            return False
+        self.states, self.lnprob, _ = self.sampler.run_mcmc(self.states, 1, lnprob0=self.lnprob)
+        return bool(np.any(before != np.asarray(self.states)))
 
     def set_scales(self, scales):
-        self.scales = np.ones(self.state.Nvars)
-        keys = self.state.get_rawkeys()
-        for i, k in enumerate(keys):
-            if k in scales:
-                self.scales[i] = scales[k]
+        self.scales = _scale_vector(self.state, scales)
 
 
 class Mh(Mcmc):
-    """Metropolis-Hastings (mcmc.py:80-121)."""
+    """Metropolis-Hastings with an axis-aligned Gaussian proposal (mcmc.py:80-121).  Draw order per step, as in the
+    reference: normal(size=Nvars) for the proposal, then -- only when the proposal passes the hard prior and
+    integrates without an encounter -- one uniform() for the accept test."""
 
     def __init__(self, initial_state, obs):
-        super(Mh, self).__init__(initial_state, obs)
+        Mcmc.__init__(self, initial_state, obs)
         self.step_size = 3e-5
         self.scales = np.ones(self.state.Nvars)
 
-    def generate_proposal(self):
-        prop = self.state.deepcopy()
-        shift = self.step_size * self.scales * np.random.normal(size=self.state.Nvars)
-        prop.shift_params(shift)
-        return prop
-
     def set_scales(self, scales):
-        self.scales = np.ones(self.state.Nvars)
-        keys = self.state.get_rawkeys()
-        for i, k in enumerate(keys):
-            if k in scales:
-                self.scales[i] = scales[k]
+        self.scales = _scale_vector(self.state, scales)
+
+    def generate_proposal(self):
+        candidate = self.state.deepcopy()
+        candidate.shift_params(self.step_size * self.scales * np.random.normal(size=self.state.Nvars))
+        return candidate
 
     def step(self):
-        while True:
-            try:
-                logp = self.state.get_logp(self.obs)
-                proposal = self.generate_proposal()
-                if proposal.priorHard():
-                    return False
-                logp_proposal = proposal.get_logp(self.obs)
-                if np.exp(logp_proposal - logp) > np.random.uniform():
-                    self.state = proposal
-                    return True
+        try:
+            current = self.state.get_logp(self.obs)
+            candidate = self.generate_proposal()
+            if candidate.priorHard():
                 return False
-            except Encounter:
-                print("Collision! {t}".format(t=datetime.utcnow()))
-                return False
+            if np.exp(candidate.get_logp(self.obs) - current) > np.random.uniform():
+                self.state = candidate
+                return True
+            return False
+        except Encounter:
+            return _collision()
 
 
 class Smala(Mcmc):
-    """Simplified manifold MALA with the SoftAbs metric (mcmc.py:126-187)."""
+    """Simplified manifold MALA with the SoftAbs metric (mcmc.py:126-187).
+
+    At a state with log-posterior derivatives (g, H): G = softabs(H), proposal N(mu, eps^2 G^-1) with
+    mu = theta + eps^2 G^-1 g / 2.  One value+gradient+Hessian evaluation (State.get_logp_d_dd) per step."""
 
     def __init__(self, initial_state, obs, eps, alp):
-        super(Smala, self).__init__(initial_state, obs)
+        Mcmc.__init__(self, initial_state, obs)
         self.epsilon = eps
         self.alpha = alp
 
     def softabs(self, hessians):
+        """Q diag(lam / tanh(alpha lam)) Q^T of -H (mcmc.py:135-139)."""
         lam, Q = np.linalg.eig(-hessians)
-        lam_twig = lam * 1. / np.tanh(self.alpha * lam)
-        H_twig = np.dot(Q, np.dot(np.diag(lam_twig), Q.T))
-        return H_twig
+        return np.dot(Q, np.dot(np.diag(lam * 1. / np.tanh(self.alpha * lam)), Q.T))
 
-    def generate_proposal(self):
-        logp, logp_d, logp_dd = self.state.get_logp_d_dd(self.obs)
-        Ginv = np.linalg.inv(self.softabs(logp_dd))
-        Ginvsqrt = np.linalg.cholesky(Ginv)
-        mu = self.state.get_params() + (self.epsilon) ** 2 * np.dot(Ginv, logp_d) / 2.
-        newparams = mu + self.epsilon * np.dot(Ginvsqrt, np.random.normal(0., 1., self.state.Nvars))
-        prop = self.state.deepcopy()
-        prop.set_params(newparams)
-        return prop
+    def _kernel(self, state, derivs):
+        """Mean and inverse metric of the proposal launched from `state`; derivs() -> (logp, g, H)."""
+        _, grad, hess = derivs(state)
+        Ginv = np.linalg.inv(self.softabs(hess))
+        return state.get_params() + (self.epsilon) ** 2 * np.dot(Ginv, grad) / 2., Ginv
 
-    def transitionProbability(self, state_from, state_to):
+    def _fresh(self, state):
+        return state.get_logp_d_dd(self.obs)
+
+    def _draw(self, derivs, carry=False):
+        mu, Ginv = self._kernel(self.state, derivs)
+        root = np.linalg.cholesky(Ginv)
+        candidate = self.state.deepcopy()
+        candidate.set_params(mu + self.epsilon * np.dot(root, np.random.normal(0., 1., self.state.Nvars)))
+        if carry:          # Alsmala's MALA step hands the stale derivatives on (mcmc.py:205-206)
+            candidate.logp_d, candidate.logp_dd = self.state.logp_d, self.state.logp_dd
+        return candidate
+
+    def _density(self, state_from, state_to, derivs):
         from scipy import stats
-        logp, logp_d, logp_dd = state_from.get_logp_d_dd(self.obs)
-        Ginv = np.linalg.inv(self.softabs(logp_dd))
-        mu = state_from.get_params() + (self.epsilon) ** 2 * np.dot(Ginv, logp_d) / 2.
+        mu, Ginv = self._kernel(state_from, derivs)
         return stats.multivariate_normal.logpdf(state_to.get_params(), mean=mu, cov=(self.epsilon) ** 2 * Ginv)
 
-    def step(self):
-        while True:
-            try:
-                stateStar = self.generate_proposal()
-                if stateStar.priorHard():
-                    return False
-                q_ts_t = self.transitionProbability(self.state, stateStar)
-                q_t_ts = self.transitionProbability(stateStar, self.state)
-                break
-            except Encounter:
-                print("Collision! {t}".format(t=datetime.utcnow()))
+    def generate_proposal(self):
+        return self._draw(self._fresh)
+
+    def transitionProbability(self, state_from, state_to):
+        return self._density(state_from, state_to, self._fresh)
+
+    def _transition(self, draw, density):
+        """Shared accept logic of step / step_mala (mcmc.py:167-187, 214-234)."""
+        star = None
+        try:
+            star = draw()
+            if star.priorHard():
                 return False
-            except np.linalg.LinAlgError:
-                print("np.linalg.linalg.LinAlgErrorhas occured, investigate later...")
-                print(stateStar.get_params())
-                print(self.state.get_params())
-                raise SystemExit(1)     # the reference calls quit() (mcmc.py:183)
-        if np.exp(stateStar.logp - self.state.logp + q_t_ts - q_ts_t) > np.random.uniform():
-            self.state = stateStar
+            forward = density(self.state, star)
+            backward = density(star, self.state)
+        except Encounter:
+            return _collision()
+        except np.linalg.LinAlgError:
+            print("np.linalg.linalg.LinAlgErrorhas occured, investigate later...")
+            if star is not None:
+                print(star.get_params())
+            print(self.state.get_params())
+            raise SystemExit(1)     # the reference calls quit() here (mcmc.py:183)
+        if np.exp(star.logp - self.state.logp + backward - forward) > np.random.uniform():
+            self.state = star
             return True
         return False
+
+    def step(self):
+        return self._transition(self.generate_proposal, self.transitionProbability)
 
 
 class Alsmala(Smala):
-    """SMALA alternating with MALA steps that reuse stale derivatives (mcmc.py:191-234)."""
+    """SMALA alternating with MALA steps that reuse the gradient and Hessian of the last full step (mcmc.py:191-234):
+    a MALA step costs one plain likelihood evaluation instead of a variational one."""
 
     def __init__(self, initial_state, obs, eps, alp):
-        super(Alsmala, self).__init__(initial_state, obs, eps, alp)
+        Smala.__init__(self, initial_state, obs, eps, alp)
+
+    def _stale(self, state):
+        return state.get_logp(self.obs), state.logp_d, state.logp_dd
 
     def generate_proposal_mala(self):
-        logp, logp_d, logp_dd = self.state.get_logp(self.obs), self.state.logp_d, self.state.logp_dd
-        Ginv = np.linalg.inv(self.softabs(logp_dd))
-        Ginvsqrt = np.linalg.cholesky(Ginv)
-        mu = self.state.get_params() + (self.epsilon) ** 2 * np.dot(Ginv, logp_d) / 2.
-        newparams = mu + self.epsilon * np.dot(Ginvsqrt, np.random.normal(0., 1., self.state.Nvars))
-        prop = self.state.deepcopy()
-        prop.set_params(newparams)
-        prop.logp_d = logp_d
-        prop.logp_dd = logp_dd
-        return prop
+        return self._draw(self._stale, carry=True)
 
     def transitionProbability_mala(self, state_from, state_to):
-        from scipy import stats
-        logp, logp_d, logp_dd = state_from.get_logp(self.obs), state_from.logp_d, state_from.logp_dd
-        Ginv = np.linalg.inv(self.softabs(logp_dd))
-        mu = state_from.get_params() + (self.epsilon) ** 2 * np.dot(Ginv, logp_d) / 2.
-        return stats.multivariate_normal.logpdf(state_to.get_params(), mean=mu, cov=(self.epsilon) ** 2 * Ginv)
+        return self._density(state_from, state_to, self._stale)
 
     def step_mala(self):
-        while True:
-            try:
-                stateStar = self.generate_proposal_mala()
-                if stateStar.priorHard():
-                    return False
-                q_ts_t = self.transitionProbability_mala(self.state, stateStar)
-                q_t_ts = self.transitionProbability_mala(stateStar, self.state)
-                break
-            except Encounter:
-                print("Collision! {t}".format(t=datetime.utcnow()))
-                return False
-            except np.linalg.LinAlgError:
-                print("np.linalg.linalg.LinAlgErrorhas occured, investigate later...")
-                print(stateStar.get_params())
-                print(self.state.get_params())
-                raise SystemExit(1)
-        if np.exp(stateStar.logp - self.state.logp + q_t_ts - q_ts_t) > np.random.uniform():
-            self.state = stateStar
-            return True
-        return False
+        return self._transition(self.generate_proposal_mala, self.transitionProbability_mala)

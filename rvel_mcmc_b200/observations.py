@@ -33,56 +33,64 @@ class Observation(object):
         return h
 
 
+def _join_legs(obs):
+    """Flat (backward, forward) views the plotting / saving helpers use (observations.py:48-50, 66-68)."""
+    obs.t = np.concatenate((obs.tb, obs.tf))
+    obs.rv = np.concatenate((obs.rvb, obs.rvf))
+    obs.err = np.concatenate((obs.errorb, obs.errorf))
+
+
 class FakeObservation(Observation):
     def __init__(self, state, Npoints=30, error=0., errorVar=0., tmax=1.5):
-        """Generates fake observations (observations.py:18-50).
+        """Synthetic data from a known State (observations.py:18-50): Npoints/2 + 1 forward epochs (t = 0 first) and
+        Npoints/2 backward epochs, uniform in +-tmax/2 and sorted; per-epoch error bar error + N(0, errorVar) and
+        velocity vx + N(0, error bar).
 
-        One simulation without an encounter distance visits obs.tf in order and then obs.tb in order
-        (observations.py:38-46); numpy's global RNG is consumed in the reference's order: tf times,
-        tb times, then (err, noise) per forward epoch, then per backward epoch.
-        """
+        numpy's legacy global RNG is consumed exactly as in the reference -- uniform(tf), uniform(tb), then one
+        (error, noise) pair of normals per forward epoch, then per backward epoch -- here as ONE standard_normal block,
+        which is the same stream (normal(m, s) is m + s * gauss()).  The noiseless velocities come from one GPU
+        integration without an encounter distance that visits tf in order, then tb in order (observations.py:26-46)."""
         self.Npoints = Npoints
         self.error = error
         self.errorVar = errorVar
-        nh = int(self.Npoints / 2.)
-        self.tf = np.append([0], np.sort(np.random.uniform(0., tmax / 2., nh)))
-        self.tb = np.sort(np.random.uniform(0., -tmax / 2., nh))
-        times = np.concatenate((self.tf, self.tb))
-        vx = state._rv_no_encounter_check(times)
-        self.rvf = np.zeros(nh + 1)
-        self.rvb = np.zeros(nh)
-        self.errorf = np.zeros(nh + 1)
-        self.errorb = np.zeros(nh)
-        for i in range(len(self.tf)):
-            self.errorf[i] = error + np.random.normal(0., self.errorVar)
-            self.rvf[i] = vx[i] + np.random.normal(0., self.errorf[i])
-        for i in range(len(self.tb)):
-            self.errorb[i] = error + np.random.normal(0., self.errorVar)
-            self.rvb[i] = vx[nh + 1 + i] + np.random.normal(0., self.errorb[i])
-        self.t = np.concatenate((self.tb, self.tf), axis=0)
-        self.rv = np.concatenate((self.rvb, self.rvf), axis=0)
-        self.err = np.concatenate((self.errorb, self.errorf), axis=0)
+        half = int(Npoints / 2.)
+        self.tf = np.concatenate(([0.], np.sort(np.random.uniform(0., tmax / 2., half))))
+        self.tb = np.sort(np.random.uniform(0., -tmax / 2., half))
+        vx = state._rv_no_encounter_check(np.concatenate((self.tf, self.tb)))
+        z = np.random.standard_normal(2 * (2 * half + 1)).reshape(-1, 2)
+        bars = error + self.errorVar * z[:, 0]
+        noisy = vx + bars * z[:, 1]
+        self.errorf, self.errorb = bars[:half + 1].copy(), bars[half + 1:].copy()
+        self.rvf, self.rvb = noisy[:half + 1].copy(), noisy[half + 1:].copy()
+        _join_legs(self)
 
 
 def parse_vels(filename):
     """Three space-delimited columns: time [day], rv [m/s], err [m/s] (observations.py:57-59)."""
-    data = np.genfromtxt(filename, usecols=(0, 1, 2), dtype='d')
-    data = np.atleast_2d(data)
+    data = np.atleast_2d(np.genfromtxt(filename, usecols=(0, 1, 2), dtype='d'))
     return data[:, 0].copy(), data[:, 1].copy(), data[:, 2].copy()
+
+
+def write_vels(filename, obs):
+    """Inverse of Observation_FromFile's unit conversion: code units back to day, m/s, m/s (time origin = last backward
+    epoch).  The reference's driver.save_obs writes the velocity column twice instead of the errors (driver.py:222); this
+    writes the three columns a .vels file is read with."""
+    np.savetxt(filename, np.column_stack((obs.t / DAY_TO_CODE, obs.rv / MS_TO_CODE, obs.err / MS_TO_CODE)), fmt="%.10g")
+
+
+DAY_TO_CODE = 0.01720      # day -> yr/2pi           (observations.py:60)
+MS_TO_CODE = 3.355e-5      # m/s -> AU/(yr/2pi)      (observations.py:61-62)
 
 
 class Observation_FromFile(Observation):
     def __init__(self, filename='yourfile.txt', Npoints=30):
-        """Load observations from a .vels or .txt file (observations.py:52-69): unit factors 0.01720 and
-        3.355e-5, np.array_split into a backward and a forward half, shift so the last backward epoch is 0."""
-        readtimes, readrvs, readerrors = parse_vels(filename)
-        readb, readf = np.array_split(readtimes * 0.01720, 2)
-        shift = readb[len(readb) - 1]
+        """Observations from a .vels / .txt file (observations.py:52-69): unit factors 0.01720 and 3.355e-5, the rows
+        split by np.array_split into a backward and a forward half, times shifted so the last backward epoch is 0.
+        Npoints is the caller's normaliser (driver.read_obs passes 100 whatever the row count)."""
+        days, ms, ms_err = parse_vels(filename)
         self.Npoints = Npoints
-        self.tf = readf - shift
-        self.tb = readb - shift
-        self.rvb, self.rvf = np.array_split(readrvs * 3.355e-5, 2)
-        self.errorb, self.errorf = np.array_split(readerrors * 3.355e-5, 2)
-        self.t = np.concatenate((self.tb, self.tf), axis=0)
-        self.rv = np.concatenate((self.rvb, self.rvf), axis=0)
-        self.err = np.concatenate((self.errorb, self.errorf), axis=0)
+        tb, tf = np.array_split(days * DAY_TO_CODE, 2)
+        self.tb, self.tf = tb - tb[-1], tf - tb[-1]
+        self.rvb, self.rvf = np.array_split(ms * MS_TO_CODE, 2)
+        self.errorb, self.errorf = np.array_split(ms_err * MS_TO_CODE, 2)
+        _join_legs(self)

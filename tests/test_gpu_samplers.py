@@ -183,3 +183,17 @@ def test_fused_device_drivers_agree_with_each_other():
     assert driver.ac_times(bs).max() <= 3                                       # SMALA AC 1/1/1 in the notebook
     # the truth is recovered
     assert abs(cs[:, 0].mean() - 0.2275) < 4 * cs[:, 0].std()
+
+
+def test_reference_api_smala_and_alsmala_step_by_step():
+    """mcmc.Smala / mcmc.Alsmala through driver.run_smala / run_alsmala (one Python iteration per step, numpy RNG)."""
+    from rvel_mcmc_b200 import observations, state, driver
+    np.random.seed(5)
+    true_state = state.State([{"a": 0.2275, "h": 0., "k": 0., "m": 0.001965}], ignore_vars=["m"])
+    obs = observations.FakeObservation(true_state, Npoints=70, error=3.5e-4, errorVar=9e-5, tmax=1.37)
+    bs, _ = driver.run_smala("t", 60, true_state, obs, 1.2, 0.14, printing_every=1000)
+    assert bs.mcmc_chain.shape == (61, 3) and np.isfinite(bs.mcmc_chainlogp).all()
+    assert 15 < len(np.unique(bs.mcmc_chain[:, 0])) <= 61                     # acceptance ~65 % in the notebook
+    ba, _ = driver.run_alsmala("t", 60, true_state, obs, 1.2, 0.14, 3.0, 0.0, printing_every=1000)
+    assert ba.mcmc_chain.shape == (61, 3) and len(np.unique(ba.mcmc_chain[:, 0])) > 10
+    assert ba.mcmc.state.logp_d is not None and ba.mcmc.state.logp_dd.shape == (3, 3)

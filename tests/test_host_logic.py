@@ -100,3 +100,17 @@ def test_autocorrelation_helpers():
     tau = driver.ac_time(x)
     assert 4 <= tau <= 10            # 0.9^k < 0.5 at k = 7
     assert abs(driver.auto_correlation(x)[0] - 1.0) < 1e-12
+
+
+def test_vels_write_read_round_trip(tmp_path):
+    # on-disk format either side of the path (observations.py:52-69, driver.py:215-222)
+    import os
+    from rvel_mcmc_b200 import observations
+    o = observations.Observation_FromFile(os.path.join(T.GOLDEN, "HD155358.vels"), Npoints=100)
+    assert len(o.tb) == 61 and len(o.tf) == 61 and o.tb[-1] == 0.0 and o.Npoints == 100
+    assert np.array_equal(o.t, np.concatenate((o.tb, o.tf))) and len(o.rv) == 122 and len(o.err) == 122
+    f = str(tmp_path / "copy.vels")
+    observations.write_vels(f, o)
+    o2 = observations.Observation_FromFile(f, Npoints=100)
+    for name in ("tf", "tb", "rvf", "rvb", "errorf", "errorb"):
+        assert np.allclose(getattr(o, name), getattr(o2, name), rtol=1e-8, atol=1e-12), name
