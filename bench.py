@@ -105,19 +105,24 @@ def run_ess(ctx, model, oh):
         c = chain[burn:]
         n_eff, tau = ess(c)
         ac_ref = max(driver.ac_time(c[:, 0, i]) for i in range(c.shape[2]))     # driver.py:366-377 (first lag with AC < 0.5)
-        out[name] = {"walkers": int(chain.shape[1]), "steps": int(chain.shape[0]), "seconds": seconds,
-                     "evals_per_s": evals / seconds, "tau_int_max": tau, "ac_time_ref_max": ac_ref,
-                     "ess_per_s": n_eff * (chain.shape[0] / c.shape[0]) / seconds}
+        # ESS of the post-burn-in samples divided by the WHOLE run time (burn-in included); tau in recorded rows
+        out[name] = {"walkers": int(chain.shape[1]), "recorded_rows": int(chain.shape[0]), "seconds": seconds,
+                     "evals_per_s": evals / seconds, "tau_int_max_rows": tau, "ac_time_ref_max_rows": ac_ref,
+                     "ess_per_s": n_eff / seconds}
 
-    W, n = 8192, 400
+    # walker counts that fill the machine: 3 CTAs x 64 lane groups per SM, one (walker, leg) item per group
+    slots = ctx.device_info()["sm_count"] * 3 * 64
+    W, n = 2 * slots, 300                   # each half-ensemble = one backward + one forward round
     t0 = time.perf_counter()
-    r = model.stretch_run(oh, walker_ball(W, 5), n, seed=11, thin=1)
-    summarise("stretch", r["chain"], time.perf_counter() - t0, W * (n + 1), n // 4)
-    W, n = 8192, 400
+    r = model.stretch_run(oh, walker_ball(W, 5), n, seed=11, thin=2)
+    summarise("stretch", r["chain"], time.perf_counter() - t0, W * (n + 1), n // 8)
+    out["stretch"]["thin"] = 2
+    W, n = slots, 300
     t0 = time.perf_counter()
-    r = model.mh_run(oh, walker_ball(W, 6), sc, 0.1, n, seed=12, thin=1)
-    summarise("mh", r["chain"], time.perf_counter() - t0, W * (n + 1), n // 4)
-    W, n = 2048, 60
+    r = model.mh_run(oh, walker_ball(W, 6), sc, 0.1, n, seed=12, thin=2)
+    summarise("mh", r["chain"], time.perf_counter() - t0, W * (n + 1), n // 8)
+    out["mh"]["thin"] = 2
+    W, n = 2368, 60
     t0 = time.perf_counter()
     r = model.smala_run(oh, walker_ball(W, 7), 0.025, 1.4, n, seed=13, thin=1)
     summarise("smala", r["chain"], time.perf_counter() - t0, W * (n + 1), n // 4)
