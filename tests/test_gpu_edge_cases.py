@@ -132,3 +132,31 @@ def test_large_batch_properties(ctx):
     perm = np.random.RandomState(0).permutation(W)
     l2, s2 = m.loglik(oh, theta[perm])
     assert np.array_equal(l2, l1[perm]) and np.array_equal(s2, s1[perm])
+
+
+def test_massive_planets_star_in_norm(ctx):
+    from test_hostmirror import _massive_system
+    E, fp, fe, obs, theta = _massive_system()
+    oh = _oh(ctx, obs)
+    m = _m(ctx, E, fp, fe, 0.0)
+    lg, sg = m.loglik(oh, theta)
+    lo, so, _ = T.orc_logp_batch(E, fp, fe, 0.0, obs, theta)
+    assert np.array_equal(sg, so) and np.abs(lg - lo).max() < 1e-9 * np.abs(lo).max()
+    lg2, gg, hg, sg2 = m.loglik_d_dd(oh, theta)
+    lo2, go, ho, so2, _ = T.orc_logp_d_dd_batch(E, fp, fe, 0.0, obs, theta)
+    assert (sg2 == 0).all() and np.abs(gg - go).max() < 1e-6 * np.abs(go).max() and np.abs(hg - ho).max() < 1e-6 * np.abs(ho).max()
+
+
+def test_non_finite_parameters_are_reported_not_hung(ctx):
+    obs = T.load_vels("HD155358.vels")
+    oh = _oh(ctx, obs)
+    m = _m(ctx, Z2, T.FP10, T.FE10, 2.0)
+    theta = np.tile(np.array(T.HD_SOL), (6, 1))
+    theta[0, 0] = np.nan; theta[1, 4] = np.inf; theta[2, 3] = np.nan; theta[3, 1] = np.nan; theta[4, 5] = -np.inf
+    lg, sg = m.loglik(oh, theta)
+    assert sg[5] == 0 and (sg[:5] != 0).all() and np.isneginf(lg[:5]).all()
+    lg, gg, hg, sg = m.loglik_d_dd(oh, theta)
+    assert sg[5] == 0 and (sg[:5] != 0).all() and np.isneginf(lg[:5]).all()
+    m.set_option("integrator", 1); m.set_option("dt0", 0.1)
+    lg, sg = m.loglik(oh, theta)
+    assert sg[5] == 0 and (sg[:5] != 0).all()

@@ -84,3 +84,30 @@ def test_mirror_monotone_backward_option():
     assert np.array_equal(s0, s1) and (s0 == 0).all()
     assert np.abs(l1 - l0).max() < 1e-9
     assert c1[1] < 0.75 * c0[1]           # 1244 -> 637 backward steps
+
+
+def _massive_system():
+    # planets as heavy as the star: sum(m_p)/m_star >= 1, so the STAR can set the IAS15 error norms (rebound takes the
+    # maxima over all particles; the kernels derive the star from the planets and switch its terms on for this case)
+    planets = [{"m": 0.6, "a": 1.0, "h": 0.05, "k": 0.0, "l": 0.3}, {"m": 0.7, "a": 4.0, "h": 0.0, "k": 0.1, "l": 2.0}]
+    E = T.elems_from_planets(planets)
+    rng = np.random.RandomState(1)
+    obs = T.Obs()
+    obs.tf = np.concatenate([[0.0], np.sort(rng.uniform(0, 20, 15))]); obs.tb = np.sort(rng.uniform(-20, 0, 15))
+    obs.rvf = 0.1 * rng.normal(size=16); obs.rvb = 0.1 * rng.normal(size=15)
+    obs.errorf = np.full(16, 0.05); obs.errorb = np.full(15, 0.05); obs.Npoints = 30
+    theta = np.array([[1.0, 4.0], [1.02, 3.9], [0.97, 4.2]])
+    return E, [0, 1], [1, 1], obs, theta
+
+
+def test_mirror_massive_planets_star_in_norm():
+    E, fp, fe, obs, theta = _massive_system()
+    lo, so, co = T.orc_logp_batch(E, fp, fe, 0.0, obs, theta)
+    lm, sm, cm = T.mirror_loglik(E, fp, fe, 0.0, obs, theta)
+    assert np.array_equal(so, sm) and (so == 0).all()
+    assert np.abs(lm - lo).max() < 1e-9 * np.abs(lo).max()
+    assert abs(co[1] - cm[1]) <= 3
+    lo2, go, ho, so2, _ = T.orc_logp_d_dd_batch(E, fp, fe, 0.0, obs, theta)
+    lm2, gm, hm, sm2, _ = T.mirror_loglik_d_dd(E, fp, fe, 0.0, obs, theta)
+    assert (sm2 == 0).all() and np.abs(lm2 - lo2).max() < 1e-9 * np.abs(lo2).max()
+    assert np.abs(gm - go).max() < 1e-8 * np.abs(go).max() and np.abs(hm - ho).max() < 1e-8 * np.abs(ho).max()
