@@ -208,39 +208,91 @@ def ac_time(series):
 
 
 def ac_times(bundle):
-    """Per-parameter AC times; for ensemble chains the mean over walkers (driver.py:355-370)."""
-    chain = bundle.mcmc_chain
-    nv = chain.shape[1]
-    out = np.zeros(nv)
+    """Per-parameter AC times as plot_ACTimes computes them (driver.py:343-382): an ensemble bundle uses mcmc_chain and
+    averages the per-walker AC times (walker-major blocks of Niter/Nwalkers rows); a single chain uses the trimmed chain
+    (mcmc_trimmedchain) when one is set, else the whole chain.  Stored on bundle.mcmc_actimes and returned."""
     if bundle.mcmc_is_emcee:
+        chain = bundle.mcmc_chain
         nw = bundle.mcmc_Nwalkers
         per = chain.shape[0] // nw
-        for j in range(nv):
-            out[j] = np.mean([ac_time(chain[w * per:(w + 1) * per, j]) for w in range(nw)])
+        out = np.array([np.mean([ac_time(chain[w * per:(w + 1) * per, j]) for w in range(nw)])
+                        for j in range(chain.shape[1])])
     else:
-        for j in range(nv):
-            out[j] = ac_time(chain[:, j])
+        chain = bundle.mcmc_trimmedchain if bundle.mcmc_trimmedchain is not None else bundle.mcmc_chain
+        out = np.array([float(ac_time(chain[:, j])) for j in range(chain.shape[1])])
     bundle.mcmc_actimes = out
     return out
 
 
-def efficacy(bundle):
-    """Niter / (wall seconds * max AC time) (driver.py:412-414)."""
-    dt = (bundle.mcmc_clocktimes[-1] - bundle.mcmc_clocktimes[0]).total_seconds()
-    act = bundle.mcmc_actimes if bundle.mcmc_actimes is not None else ac_times(bundle)
-    return bundle.mcmc_Niter / (dt * np.max(act))
+def plot_ACTimes(bundle, size=None, name='Name_left_empty', save=False):
+    """The reference's entry point for AC times (driver.py:343-382) without the figure: prints and stores them."""
+    act = ac_times(bundle)
+    for t in act:
+        print("AC time {t}".format(t=t))
+    return act
 
 
-def calc_kstatistic(chain_a, chain_b):
-    """Two-sample KS statistic per parameter (driver.py:423-425)."""
+def efficacy(Niter, AC, clockTimes):
+    """Niter / (wall seconds * max AC time), wall clock from the SECOND stamp to the last (driver.py:412-414)."""
+    dt = (clockTimes[len(clockTimes) - 1] - clockTimes[1]).total_seconds()
+    return (Niter / (dt * np.amax(AC)))
+
+
+def calc_kstatistic(chain1, chain2, verbose=False):
+    """Two-sample KS test per parameter (driver.py:423-425 prints scipy's result; here the D statistics are returned)."""
     from scipy import stats
-    return [stats.ks_2samp(chain_a[:, i], chain_b[:, i])[0] for i in range(chain_a.shape[1])]
+    out = []
+    for i in range(len(np.transpose(chain1))):
+        r = stats.ks_2samp(np.transpose(chain1)[i], np.transpose(chain2)[i])
+        if verbose:
+            print(r)
+        out.append(r[0])
+    return out
 
 
-def save_data(bundle, h):
-    np.save('chain_{ha}.npy'.format(ha=h.hexdigest()), bundle.mcmc_chain)
-    np.save('chainlogp_{ha}.npy'.format(ha=h.hexdigest()), bundle.mcmc_chainlogp)
+# ---- persistence (driver.py:46-54, 429-448): same file names and formats as the reference ------------------------
+
+def save_data(dat, name, h):
+    """np.save of one array under '<name>_<md5>.npy' (driver.py:432-433)."""
+    np.save('{n}_{h}'.format(n=name, h=h.hexdigest()), dat)
 
 
-def load_data(hexdigest):
-    return np.load('chain_{ha}.npy'.format(ha=hexdigest)), np.load('chainlogp_{ha}.npy'.format(ha=hexdigest))
+def load_data(name, h):
+    """Inverse of save_data (driver.py:429-430)."""
+    return np.load('{n}_{h}.npy'.format(n=name, h=h.hexdigest()))
+
+
+def save_bundle(bundle, h):
+    """chain, chainlogp and clocktimes of a bundle, the three arrays the notebooks store per run."""
+    save_data(bundle.mcmc_chain, "chain", h)
+    save_data(bundle.mcmc_chainlogp, "chainlogp", h)
+    save_data(np.array([t.isoformat() for t in bundle.mcmc_clocktimes]), "clocktimes", h)
+
+
+def writing_to_log(obj, name, logging):
+    """Append every element of `obj` (np.ndenumerate order), space separated, as one line of 'log<name>'
+    (driver.py:46-54, mcmc_benchmark_mh.py:21-28; the reference's version raises NameError on a typo)."""
+    if not logging:
+        return
+    with open("log{r}".format(r=name), "a") as a:
+        for _, value in np.ndenumerate(obj):
+            a.write("{v} ".format(v=value))
+        a.write("\n")
+
+
+def _save_aux(h, true_state, line):
+    with open('aux_{h}'.format(h=h.hexdigest()), "w") as text_file:
+        text_file.write('initial = ' + str(true_state.planets))
+        text_file.write(line)
+
+
+def save_aux_smala(h, true_state, label, Niter, eps, alpha):
+    _save_aux(h, true_state, "\nlabel, Niter, Eps, Alpha = '{l}', {n}, {e}, {a}".format(l=label, n=Niter, e=eps, a=alpha))
+
+
+def save_aux_emcee(h, true_state, label, Niter, Nwalkers, scal):
+    _save_aux(h, true_state, "\nlabel, Niter, Nwalkers, Scale = '{l}', {n}, {s}, {t}".format(l=label, n=Niter, s=Nwalkers, t=scal))
+
+
+def save_aux_mh(h, true_state, label, Niter, scal, step):
+    _save_aux(h, true_state, "\nlabel, Niter, Scale, Stepsize = '{l}', {n}, {s}, {t}".format(l=label, n=Niter, s=scal, t=step))

@@ -114,3 +114,41 @@ def test_vels_write_read_round_trip(tmp_path):
     o2 = observations.Observation_FromFile(f, Npoints=100)
     for name in ("tf", "tb", "rvf", "rvb", "errorf", "errorb"):
         assert np.allclose(getattr(o, name), getattr(o2, name), rtol=1e-8, atol=1e-12), name
+
+
+def test_driver_persistence_formats(tmp_path, monkeypatch):
+    # driver.py:46-54, 429-448: '<name>_<md5>.npy' dumps, 'log<name>' lines, 'aux_<md5>' notes
+    from rvel_mcmc_b200 import driver, state
+    monkeypatch.chdir(tmp_path)
+    st = state.State([{"a": 0.35, "m": 0.001965}], ignore_vars=["m"])
+    h = driver._run_id(st, "label")
+    chain = np.arange(12.0).reshape(4, 3)
+    driver.save_data(chain, "chain", h)
+    assert np.array_equal(driver.load_data("chain", h), chain)
+    driver.writing_to_log(chain[:2], "_t", True)
+    driver.writing_to_log("START", "_t", True)
+    driver.writing_to_log(chain, "_t", False)
+    lines = open("log_t").read().split("\n")
+    assert lines[0].split() == ["0.0", "1.0", "2.0", "3.0", "4.0", "5.0"] and lines[1].strip() == "START" and len(lines) == 3
+    driver.save_aux_mh(h, st, "label", 100, {"a": 3e-4}, 5)
+    txt = open("aux_" + h.hexdigest()).read()
+    assert txt.startswith("initial = [{") and "label, Niter, Scale, Stepsize = 'label', 100" in txt
+
+
+def test_ac_times_and_efficacy_definitions():
+    # driver.py:343-382 (AC time = first lag with normalised autocorrelation < 0.5) and :412-414 (efficacy)
+    from datetime import datetime, timedelta
+    from rvel_mcmc_b200 import driver
+    rng = np.random.RandomState(0)
+    x = np.zeros((4000, 2))
+    for i in range(1, len(x)):
+        x[i, 0] = 0.9 * x[i - 1, 0] + rng.normal()          # AC(lag) = 0.9^lag -> first lag below 0.5 is 7
+        x[i, 1] = rng.normal()
+    b = driver.McmcBundle(None, x, np.zeros(len(x)), [], None, len(x), None, trimmedchain=x[500:])
+    act = driver.plot_ACTimes(b, (1, 1))
+    assert 5 <= act[0] <= 9 and act[1] == 1 and b.mcmc_actimes is act
+    be = driver.McmcBundle(None, np.concatenate([x, x]), None, [], None, 2 * len(x), None, is_emcee=True, Nwalkers=2)
+    assert np.allclose(driver.ac_times(be), [driver.ac_time(x[:, 0]), 1.0])
+    t0 = datetime(2020, 1, 1)
+    stamps = [t0, t0 + timedelta(seconds=3), t0 + timedelta(seconds=13)]
+    assert abs(driver.efficacy(1000, [2.0, 5.0], stamps) - 1000 / (10.0 * 5.0)) < 1e-12      # from the SECOND stamp
