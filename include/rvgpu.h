@@ -92,6 +92,12 @@ int rv_loglik_dev(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, const d
 int rv_rv_curve(rv_ctx* ctx, const rv_model* model, const double* theta, int64_t W, const double* times,
                 int nt, double* rv, int32_t* status);
 
+/* ---- State.setup_sim (state.py:36-47) made visible: the barycentric particles every integration starts from ---- */
+/* particles[W][n_planets+1][7] = m, x, y, z, vx, vy, vz (star first), after rebound's Pal -> cartesian conversion
+ * and move_to_com; status[W] = RV_PRIOR where priorHard() holds (the particles are still written).        */
+int rv_initial_conditions(rv_ctx* ctx, const rv_model* model, const double* theta, int64_t W, double* particles,
+                          int32_t* status);
+
 /* ---- State.get_logp_d_dd (state.py:290-294; setup_sim_vars state.py:229-248, get_chi2_d_dd state.py:253-285) ---- */
 /* theta[W][nvars] -> logp[W], grad[W][nvars], hess[W][nvars][nvars] (symmetric), status[W].  The hard prior is tested
  * first (status RV_PRIOR), as the reference's callers do (mcmc.py:171).  On a non-zero status logp = -inf and the

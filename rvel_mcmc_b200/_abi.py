@@ -50,6 +50,7 @@ _SIGNATURES = {
                                  C.c_void_p, C.c_void_p]),
     "rv_loglik_d_dd_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_void_p]),
+    "rv_initial_conditions": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "rv_rv_curve": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p,
                               C.c_void_p]),
     "rv_mh_run": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_double,
@@ -242,6 +243,17 @@ class ModelHandle(object):
                                                        C.c_void_p(d_logp), C.c_void_p(d_grad), C.c_void_p(d_hess),
                                                        C.c_void_p(d_status), C.c_void_p(stream) if stream else None),
                        "rv_loglik_d_dd_dev")
+
+    def initial_conditions(self, theta):
+        """theta[W][nvars] -> (particles[W][P+1][7] = m,x,y,z,vx,vy,vz in the barycentric frame, status[W]);
+        what State.setup_sim builds (state.py:36-47)."""
+        theta = self._theta(theta)
+        W = theta.shape[0]
+        out = np.zeros((W, self.n_planets + 1, 7), dtype=np.float64)
+        status = np.empty(W, dtype=np.int32)
+        self.ctx.check(self.ctx.lib.rv_initial_conditions(self.ctx.h, self.h, _ptr(theta), W, _ptr(out), _ptr(status)),
+                       "rv_initial_conditions")
+        return out, status
 
     def rv_curve(self, theta, times):
         """theta[W][nvars], times[nt] -> (rv[W][nt], status[W]); State.get_rv for a batch."""

@@ -330,6 +330,28 @@ int rv_rv_curve(rv_ctx* ctx, const rv_model* model, const double* theta, int64_t
     return 0;
 }
 
+int rv_initial_conditions(rv_ctx* ctx, const rv_model* model, const double* theta, int64_t W, double* particles,
+                          int32_t* status) {
+    if (!ctx || !model) return fail(ctx, -1, "rv_initial_conditions: NULL handle");
+    if (W < 0) return fail(ctx, -2, "rv_initial_conditions: negative W");
+    if (W == 0) return 0;
+    if (!particles || !status) return fail(ctx, -1, "rv_initial_conditions: NULL buffer");
+    CU(ctx, cudaSetDevice(ctx->device));
+    const size_t nv = (size_t)(model->h.nvars > 0 ? model->h.nvars : 1);
+    const size_t np7 = (size_t)(model->h.P + 1) * 7;
+    if (int rc = ensure(ctx, &ctx->d_theta, &ctx->cap_theta, (size_t)W * nv)) return rc;
+    if (int rc = ensure(ctx, &ctx->d_rv, &ctx->cap_rv, (size_t)W * np7)) return rc;
+    if (int rc = ensure(ctx, &ctx->d_status, &ctx->cap_status, (size_t)W)) return rc;
+    cudaStream_t s = ctx->stream;
+    if (model->h.nvars > 0)
+        CU(ctx, cudaMemcpyAsync(ctx->d_theta, theta, (size_t)W * model->h.nvars * sizeof(double), cudaMemcpyHostToDevice, s));
+    CU(ctx, rv::launch_initial_conditions(model->d, ctx->d_theta, W, ctx->d_rv, ctx->d_status, s));
+    CU(ctx, cudaMemcpyAsync(particles, ctx->d_rv, (size_t)W * np7 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CU(ctx, cudaMemcpyAsync(status, ctx->d_status, (size_t)W * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    CU(ctx, cudaStreamSynchronize(s));
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // value + gradient + Hessian
 

@@ -131,6 +131,47 @@ cudaError_t launch_curve_finalize(unsigned long long* item_counter, cudaStream_t
     return cudaGetLastError();
 }
 
+// ---- State.setup_sim (state.py:36-47) made visible: barycentric particles [W][P+1][7] = m, x, y, z, vx, vy, vz ----
+// One thread per walker; the same Pal -> cartesian and move_to_com arithmetic the integrating kernels start from.
+__global__ void initial_conditions_kernel(const Model* __restrict__ md, const double* __restrict__ theta, long long W,
+                                          double* __restrict__ out, int* __restrict__ status) {
+    const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= W) return;
+    const int P = md->P;
+    const double m0 = md->m_star;
+    double xr[MAXP][3], vr[MAXP][3], mp[MAXP];
+    double cx[3] = {0, 0, 0}, cv[3] = {0, 0, 0}, mtot = m0;
+    bool bad = false;
+    for (int i = 0; i < P; i++) {
+        double el[NELEM];
+        for (int k = 0; k < NELEM; k++) {
+            const int s = md->src[i * NELEM + k];
+            el[k] = (s >= 0) ? theta[w * md->nvars + s] : md->fixed[i * NELEM + k];
+        }
+        bad = bad || prior_hard(el);
+        pal_to_cart(el, m0, xr[i], vr[i]);
+        mp[i] = el[EL_M];
+        mtot += mp[i];
+        for (int d = 0; d < 3; d++) { cx[d] += mp[i] * xr[i][d]; cv[d] += mp[i] * vr[i][d]; }
+    }
+    double* o = out + w * (P + 1) * 7;
+    o[0] = m0;
+    for (int d = 0; d < 3; d++) { o[1 + d] = -cx[d] / mtot; o[4 + d] = -cv[d] / mtot; }
+    for (int i = 0; i < P; i++) {
+        double* q = o + (i + 1) * 7;
+        q[0] = mp[i];
+        for (int d = 0; d < 3; d++) { q[1 + d] = xr[i][d] - cx[d] / mtot; q[4 + d] = vr[i][d] - cv[d] / mtot; }
+    }
+    status[w] = bad ? ST_PRIOR : ST_OK;
+}
+
+cudaError_t launch_initial_conditions(const Model* md, const double* theta, long long W, double* out, int* status,
+                                      cudaStream_t stream) {
+    const int nt = 128;
+    initial_conditions_kernel<<<(unsigned)((W + nt - 1) / nt), nt, 0, stream>>>(md, theta, W, out, status);
+    return cudaGetLastError();
+}
+
 // ---- FP64 FMA-pipe peak microbenchmark (roofline denominator; MEASURED_PEAKS.json has no FP64 entry) ----
 __global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, double seed) {
     double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;

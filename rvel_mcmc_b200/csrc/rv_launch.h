@@ -7,6 +7,9 @@ cudaError_t launch_loglik(const LoglikArgs& a, int P, int D, int mapping, int nu
 cudaError_t launch_finalize(const double* part_chi2, const int* part_status, long long W, double npoints,
                             double* logp, int* status, unsigned long long* item_counter, cudaStream_t stream);
 cudaError_t launch_curve_finalize(unsigned long long* item_counter, cudaStream_t stream);
+struct Model;
+cudaError_t launch_initial_conditions(const Model* md, const double* theta, long long W, double* out, int* status,
+                                      cudaStream_t stream);
 cudaError_t launch_fp64_peak(double* d_out, int blocks, int iters, cudaStream_t stream);
 // variational path (rv_var_kernels.cu)
 struct VarArgs;

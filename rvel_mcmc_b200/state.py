@@ -25,6 +25,23 @@ def _py2_order(planet):
     return known + other
 
 
+class _Particle(object):
+    __slots__ = ("m", "x", "y", "z", "vx", "vy", "vz")
+
+    def __init__(self, row):
+        self.m, self.x, self.y, self.z, self.vx, self.vy, self.vz = [float(v) for v in row]
+
+
+class _SimSnapshot(object):
+    """Initial particles of a simulation (see State.setup_sim)."""
+
+    def __init__(self, rows, exit_min_distance):
+        self.particles = [_Particle(r) for r in rows]
+        self.exit_min_distance = exit_min_distance
+        self.N = len(self.particles)
+        self.t = 0.0
+
+
 class State(object):
     verbose_prior = False    # the reference prints on every prior rejection (state.py:302-313)
     # Not in the reference (which always runs rebound's default IAS15): "whfast" selects the optional fixed-step
@@ -113,10 +130,14 @@ class State(object):
 
     # ------------------------------------------------------------------ reference API
     def setup_sim(self):
-        """The reference returns a rebound.Simulation (state.py:36-47); here the set-up happens inside the
-        kernel.  Returns the barycentric initial conditions [(m,x,y,z,vx,vy,vz)] for inspection only."""
-        raise NotImplementedError("setup_sim() exposed a rebound.Simulation; the CUDA engine builds the "
-                                  "simulation on the device (use get_rv / get_logp)")
+        """The reference returns a rebound.Simulation ready to integrate (state.py:36-47).  The CUDA engine builds and
+        integrates the simulation on the device, so what is returned here is a read-only snapshot of that initial
+        simulation: `.particles` (objects with m, x, y, z, vx, vy, vz; star first, barycentric frame, i.e. after
+        move_to_com) and `.exit_min_distance`, computed by the same device code the integrating kernels start from."""
+        parts, _ = self._model().initial_conditions(self.get_params()[None, :])
+        hill = max(p["a"] * (p["m"] / 3.) ** (1. / 3.) for p in self.planets)
+        self.hillRadiusMax = hill
+        return _SimSnapshot(parts[0], self.hillRadiusFactor * hill)
 
     def _rv_no_encounter_check(self, times):
         model = self._model(hill_factor=0.0)

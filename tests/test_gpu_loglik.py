@@ -210,3 +210,25 @@ def test_monotone_backward_option_matches_default(ctx):
     assert np.array_equal(s0, s1) and (s0 == 0).all()
     assert np.abs(l1 - l0).max() < 1e-8 and abs(l1[0] - T.KAT2_LOGP) < 5e-11
     assert c1[1] < 0.75 * c0[1]
+
+
+def test_kat1_initial_conditions_on_gpu(ctx):
+    # (Ex)HD155358.ipynb:84-95 -- the 16-digit barycentric particles rebound printed, from the device's setup code
+    m = _model(ctx, np.zeros((2, 7)), T.FP10, T.FE10, 2.0)
+    parts, st = m.initial_conditions(np.array([T.HD_SOL]))
+    com = parts[0]
+    assert st[0] == 0 and com[0, 0] == 1.0
+    np.testing.assert_allclose(com[0, [4, 5]], [-0.00041883056816320016, 0.00014019875566797076], rtol=4e-15, atol=0)
+    np.testing.assert_allclose(com[0, [1, 2]], [-0.00015729068590102283, -0.00035766924337062825], rtol=4e-15, atol=0)
+    np.testing.assert_allclose(com[1, [4, 5]], [1.345239134152752, -0.31103808924058135], rtol=0, atol=6e-16)
+    np.testing.assert_allclose(com[1, [1, 2]], [-0.10055834617969424, -0.5753744383506549], rtol=0, atol=6e-16)
+    np.testing.assert_allclose(com[2, [4, 5]], [-0.9277725732029665, 0.16229778378922738], rtol=0, atol=6e-16)
+    np.testing.assert_allclose(com[2, [1, 2]], [0.2964757596787923, 1.0432799562638122], rtol=0, atol=6e-16)
+    assert np.all(com[:, [3, 6]] == 0.0)
+    # and the reference-facing view: State.setup_sim().particles[0].vx is the RV at t = 0
+    from rvel_mcmc_b200 import state
+    s = state.State(T.planets_from_vec(T.HD_SOL)); s.hillRadiusFactor = 2.
+    sim = s.setup_sim()
+    assert sim.N == 3 and abs(sim.particles[0].vx - (-0.00041883056816320016)) < 1e-18
+    assert abs(sim.particles[0].vx - s.get_rv([0.0])[0]) < 1e-18
+    assert abs(sim.exit_min_distance - 2. * 1.04404207 * (0.00083037971 / 3.) ** (1. / 3.)) < 1e-15
