@@ -319,7 +319,12 @@ def main():
         torch.cuda.synchronize()
         lg = d_logp[:sample].cpu().numpy(); sg = d_status[:sample].cpu().numpy()
         okm = (so == 0) & (sg == 0)
+        n1 = 256
+        dt1, _, _, _ = oracle_batch(obs, host_theta[2][:n1].numpy(), 1)                 # the same port on ONE core
         cpu_baseline = {"value": sample / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                        "single_core_value": n1 / dt1,
+                        "historical_reference": "16.6 evals/s: rebound + emcee under Python 2 on an unknown 2017 CPU, one core, "
+                                                "Encounter storms included ((Ex)HD155358.ipynb:181-456; BASELINE.md section 1) -- context only",
                         "sample": "%d walkers of step 0, oracle/rv_oracle.c OpenMP %d threads, %.1f s" % (sample, cores, dt),
                         "oracle_S_per_eval": cnt[0] / sample, "oracle_T_per_eval": cnt[1] / sample,
                         "parity_max_abs_logp_diff": float(np.abs(lg[okm] - lo[okm]).max()) if okm.any() else None,
