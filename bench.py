@@ -90,7 +90,7 @@ def oracle_batch(obs, theta, nthreads):
     o = T.Obs()
     o.tf, o.tb, o.rvf, o.rvb, o.errorf, o.errorb, o.Npoints = obs.tf, obs.tb, obs.rvf, obs.rvb, obs.errorf, obs.errorb, obs.Npoints
     t0 = time.perf_counter()
-    logp, st, cnt = T.orc_logp_batch(np.zeros((2, 7)), FP10, FE10, 2.0, o, theta, nthreads=nthreads)
+    logp, st, cnt = T.orc_logp_batch(np.zeros((2, 7)), FP10, FE10, 2.0, o, theta, nthreads=nthreads, lib=T.oracle_fast())
     return time.perf_counter() - t0, logp, st, cnt
 
 
@@ -153,7 +153,7 @@ def run_reference(args):
             "config": {"workload": "HD155358 2-planet log-likelihood, %d-walker sample per step (bounded CPU sample)" % sample,
                        "walkers_per_step": sample, "epochs": 122},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": "%d walkers x %d steps, oracle/rv_oracle.c (OpenMP, %d threads)" % (sample, args.steps, cores)},
+                             "sample": "%d walkers x %d steps, oracle/rv_oracle.c (gcc -O3 -march=native, OpenMP, %d threads)" % (sample, args.steps, cores)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -325,7 +325,7 @@ def main():
                         "single_core_value": n1 / dt1,
                         "historical_reference": "16.6 evals/s: rebound + emcee under Python 2 on an unknown 2017 CPU, one core, "
                                                 "Encounter storms included ((Ex)HD155358.ipynb:181-456; BASELINE.md section 1) -- context only",
-                        "sample": "%d walkers of step 0, oracle/rv_oracle.c OpenMP %d threads, %.1f s" % (sample, cores, dt),
+                        "sample": "%d walkers of step 0, oracle/rv_oracle.c (gcc -O3 -march=native) OpenMP %d threads, %.1f s" % (sample, cores, dt),
                         "oracle_S_per_eval": cnt[0] / sample, "oracle_T_per_eval": cnt[1] / sample,
                         "parity_max_abs_logp_diff": float(np.abs(lg[okm] - lo[okm]).max()) if okm.any() else None,
                         "parity_status_equal": bool(np.array_equal(so, sg))}

@@ -20,6 +20,30 @@ def oracle():
     return _oracle
 
 
+_oracle_fast = None
+
+
+def oracle_fast():
+    """The oracle sources compiled -O3 -march=native ON THIS MACHINE (timing only; bench.py's CPU legs).  The file name
+    carries a tag of the host CPU's feature flags, so a build made elsewhere is never loaded; falls back to the checker
+    build if the compiler is missing."""
+    global _oracle_fast
+    if _oracle_fast is None:
+        import hashlib
+        import subprocess
+        try:
+            flags = [l for l in open("/proc/cpuinfo") if l.startswith("flags")][0]
+        except Exception:
+            flags = "unknown"
+        name = os.path.join("_build", "librvoracle_fast_%s.so" % hashlib.md5(flags.encode()).hexdigest()[:10])
+        path = os.path.join(ROOT, "oracle", name)
+        if not os.path.exists(path):
+            subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "fast", "FAST_OUT=" + name],
+                           capture_output=True, timeout=300)
+        _oracle_fast = C.CDLL(path) if os.path.exists(path) else oracle()
+    return _oracle_fast
+
+
 def mirror():
     global _mirror
     if _mirror is None:
@@ -86,7 +110,7 @@ def orc_rv(E, hill, times):
     return st, rv
 
 
-def orc_logp_batch(fixed, fp, fe, hill, obs, theta, nthreads=8):
+def orc_logp_batch(fixed, fp, fe, hill, obs, theta, nthreads=8, lib=None):
     fixed = np.ascontiguousarray(fixed, dtype=np.float64)
     theta = np.ascontiguousarray(theta, dtype=np.float64)
     fp = np.ascontiguousarray(fp, dtype=np.int32)
@@ -95,7 +119,7 @@ def orc_logp_batch(fixed, fp, fe, hill, obs, theta, nthreads=8):
     logp = np.zeros(W)
     status = np.zeros(W, dtype=np.int32)
     cnt = (C.c_long * 3)()
-    oracle().orc_logp_batch(fixed.shape[0], vp(fixed), len(fp), vp(fp), vp(fe), C.c_double(hill),
+    (lib or oracle()).orc_logp_batch(fixed.shape[0], vp(fixed), len(fp), vp(fp), vp(fe), C.c_double(hill),
                             vp(obs.tf), vp(obs.rvf), vp(obs.errorf), len(obs.tf),
                             vp(obs.tb), vp(obs.rvb), vp(obs.errorb), len(obs.tb), C.c_double(obs.Npoints),
                             vp(theta), C.c_long(W), vp(logp), vp(status), cnt, nthreads)
