@@ -135,13 +135,19 @@ def _scale_vector(state, scal):
     return np.array([scal[k] for k in state.get_rawkeys()], dtype=np.float64)
 
 
+def _sampler_state(true_state):
+    """The state a sampler object would hold: Mcmc.__init__ deep-copies the initial state (mcmc.py:13), and the reference's
+    deepcopy builds a fresh State, so hillRadiusFactor is back to 1 for everything the sampler evaluates (state.py:212-213)."""
+    return true_state.deepcopy()
+
+
 def run_mh_gpu(label, Niter, true_state, obs, scal, step, nchains=1, seed=0):
     """`nchains` independent MH chains of Niter steps each (Mh.step semantics, mcmc.py:107-121), all started at true_state."""
     from . import _abi
     ctx = _abi.default_context()
     t0 = datetime.utcnow()
-    r = true_state._model(ctx).mh_run(obs._handle(ctx), np.tile(true_state.get_params(), (nchains, 1)),
-                                      _scale_vector(true_state, scal), step, Niter, seed=seed)
+    r = _sampler_state(true_state)._model(ctx).mh_run(obs._handle(ctx), np.tile(true_state.get_params(), (nchains, 1)),
+                                                      _scale_vector(true_state, scal), step, Niter, seed=seed)
     print("Acceptance rate: %.3f%%" % (100. * r["n_accept"].mean() / max(Niter, 1)))
     return _bundle_from_device("mh", r, "chain_logp", true_state, obs, Niter * nchains, nchains, label, t0)
 
@@ -155,7 +161,7 @@ def run_emcee_gpu(label, Niter, true_state, obs, Nwalkers, scal, seed=0):
     sc = _scale_vector(true_state, scal)
     start = np.array([true_state.get_params() + 1e-3 * sc * np.random.normal(size=true_state.Nvars) for _ in range(Nwalkers)])
     nsteps = int(Niter / Nwalkers)
-    r = true_state._model(ctx).stretch_run(obs._handle(ctx), start, nsteps, seed=seed)
+    r = _sampler_state(true_state)._model(ctx).stretch_run(obs._handle(ctx), start, nsteps, seed=seed)
     return _bundle_from_device("emcee", r, "chain_lnp", true_state, obs, Niter, Nwalkers, label, t0)
 
 
@@ -164,8 +170,8 @@ def run_smala_gpu(label, Niter, true_state, obs, eps, alpha, nchains=1, seed=0):
     from . import _abi
     ctx = _abi.default_context()
     t0 = datetime.utcnow()
-    r = true_state._model(ctx).smala_run(obs._handle(ctx), np.tile(true_state.get_params(), (nchains, 1)), eps, alpha,
-                                         Niter, seed=seed)
+    r = _sampler_state(true_state)._model(ctx).smala_run(obs._handle(ctx), np.tile(true_state.get_params(), (nchains, 1)),
+                                                         eps, alpha, Niter, seed=seed)
     print("Acceptance rate: %.3f%%" % (100. * r["n_accept"].mean() / max(Niter, 1)))
     return _bundle_from_device("smala", r, "chain_logp", true_state, obs, Niter * nchains, nchains, label, t0)
 
@@ -175,8 +181,8 @@ def run_alsmala_gpu(label, Niter, true_state, obs, eps, alpha, bern_a, bern_b=No
     from . import _abi
     ctx = _abi.default_context()
     t0 = datetime.utcnow()
-    r = true_state._model(ctx).alsmala_run(obs._handle(ctx), np.tile(true_state.get_params(), (nchains, 1)), eps, alpha,
-                                           bern_a, Niter, niter_total=Niter, seed=seed)
+    r = _sampler_state(true_state)._model(ctx).alsmala_run(obs._handle(ctx), np.tile(true_state.get_params(), (nchains, 1)),
+                                                           eps, alpha, bern_a, Niter, niter_total=Niter, seed=seed)
     print("Acceptance rate: %.3f%%" % (100. * r["n_accept"].mean() / max(Niter, 1)))
     return _bundle_from_device("alsmala", r, "chain_logp", true_state, obs, Niter * nchains, nchains, label, t0)
 
