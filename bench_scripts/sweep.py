@@ -162,9 +162,12 @@ def main():
             s = torch.cuda.current_stream().cuda_stream
             m.loglik_dev(oh, th.data_ptr(), min(hi - lo, 1024), lp.data_ptr(), stt.data_ptr(), s); torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(); m.loglik_dev(oh, th.data_ptr(), hi - lo, lp.data_ptr(), stt.data_ptr(), s); e1.record()
-            torch.cuda.synchronize()
-            sec = maxsec(e0.elapsed_time(e1) * 1e-3)
+            best = None
+            for _ in range(2):      # the first full-size call also grows the context's scratch buffers; report the second
+                e0.record(); m.loglik_dev(oh, th.data_ptr(), hi - lo, lp.data_ptr(), stt.data_ptr(), s); e1.record()
+                torch.cuda.synchronize()
+                best = e0.elapsed_time(e1) * 1e-3
+            sec = maxsec(best)
             emit({"config": "C5 sweep, HD155358-shape truth, IAS15", "walkers": W, "epochs": nep + 1, "ms": 1e3 * sec,
                   "evals_per_s": W / sec, "ok_fraction": float((stt == 0).float().mean().item())})
             if W == 10 ** 5 or args.quick:
