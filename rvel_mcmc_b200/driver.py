@@ -6,11 +6,16 @@ definitions (driver.py:37-44, 343-425).  Plot functions are out of scope (matplo
 dependency of the hot path).
 """
 import hashlib
-from datetime import datetime
+from datetime import datetime, timezone
 
 import numpy as np
 
 from . import mcmc, observations
+
+def _utcnow():
+    """Naive UTC timestamp, what the reference's datetime.utcnow() returned (driver.py:64)."""
+    return datetime.now(timezone.utc).replace(tzinfo=None)
+
 
 
 class McmcBundle(object):
@@ -50,7 +55,7 @@ def _single_chain(sampler, label, Niter, true_state, obs, printing_every, steppe
     chain = np.zeros((Niter + 1, sampler.state.Nvars))
     chainlogp = np.zeros(Niter + 1)
     tries = 0
-    clocktimes = [datetime.utcnow()]
+    clocktimes = [_utcnow()]
     chainlogp[0] = true_state.get_logp(obs)
     chain[0] = true_state.get_params()
     for i in range(Niter):
@@ -60,9 +65,9 @@ def _single_chain(sampler, label, Niter, true_state, obs, printing_every, steppe
         chain[i + 1] = sampler.state.get_params()
         if i % printing_every == 1:
             print("Progress: {p:.5}%, {n} accepted steps have been made, time: {t}".format(
-                p=100. * (float(i) / Niter), t=datetime.utcnow(), n=tries))
-            clocktimes.append(datetime.utcnow())
-    clocktimes.append(datetime.utcnow())
+                p=100. * (float(i) / Niter), t=_utcnow(), n=tries))
+            clocktimes.append(_utcnow())
+    clocktimes.append(_utcnow())
     print("Acceptance rate: %.3f%%" % ((tries / float(Niter)) * 100))
     h = _run_id(true_state, label)
     return McmcBundle(sampler, chain, chainlogp, clocktimes, obs, Niter, true_state), h
@@ -80,15 +85,15 @@ def run_emcee(label, Niter, true_state, obs, Nwalkers, scal, printing_every=400)
     nsteps = int(Niter / Nwalkers)
     listchain = np.zeros((Nwalkers, ens.state.Nvars, nsteps))
     listchainlogp = np.zeros((Nwalkers, nsteps))
-    clocktimes = [datetime.utcnow()]
+    clocktimes = [_utcnow()]
     for i in range(nsteps):
         ens.step()
         listchainlogp[:, i] = ens.lnprob
         listchain[:, :, i] = ens.states
         if i % printing_every == 1:
-            print("Progress: {p:.5}%, time: {t}".format(p=100. * (float(i) / nsteps), t=datetime.utcnow()))
-            clocktimes.append(datetime.utcnow())
-    clocktimes.append(datetime.utcnow())
+            print("Progress: {p:.5}%, time: {t}".format(p=100. * (float(i) / nsteps), t=_utcnow()))
+            clocktimes.append(_utcnow())
+    clocktimes.append(_utcnow())
     print("Error(s): {e}".format(e=ens.totalErrorCount))
     h = _run_id(true_state, label)
     # walker-major concatenation, as driver.py:108-112
@@ -125,7 +130,7 @@ def _bundle_from_device(sampler_name, r, lp_key, true_state, obs, Niter, nchains
     chain, chain_lp = r["chain"], r[lp_key]                      # [steps][W][nvars], [steps][W]
     flat = np.concatenate([chain[:, w, :] for w in range(nchains)], axis=0)
     flat_lp = np.concatenate([chain_lp[:, w] for w in range(nchains)])
-    bundle = McmcBundle(sampler_name, flat, flat_lp, [t0, datetime.utcnow()], obs, Niter, true_state, is_emcee=True,
+    bundle = McmcBundle(sampler_name, flat, flat_lp, [t0, _utcnow()], obs, Niter, true_state, is_emcee=True,
                         Nwalkers=nchains)
     bundle.device_result = r
     return bundle, _run_id(true_state, label)
@@ -145,7 +150,7 @@ def run_mh_gpu(label, Niter, true_state, obs, scal, step, nchains=1, seed=0):
     """`nchains` independent MH chains of Niter steps each (Mh.step semantics, mcmc.py:107-121), all started at true_state."""
     from . import _abi
     ctx = _abi.default_context()
-    t0 = datetime.utcnow()
+    t0 = _utcnow()
     r = _sampler_state(true_state)._model(ctx).mh_run(obs._handle(ctx), np.tile(true_state.get_params(), (nchains, 1)),
                                                       _scale_vector(true_state, scal), step, Niter, seed=seed)
     print("Acceptance rate: %.3f%%" % (100. * r["n_accept"].mean() / max(Niter, 1)))
@@ -157,7 +162,7 @@ def run_emcee_gpu(label, Niter, true_state, obs, Nwalkers, scal, seed=0):
     ensemble steps from the reference's start ball theta + 1e-3*scales*N(0,1) (mcmc.py:49-51, numpy RNG as there)."""
     from . import _abi
     ctx = _abi.default_context()
-    t0 = datetime.utcnow()
+    t0 = _utcnow()
     sc = _scale_vector(true_state, scal)
     start = np.array([true_state.get_params() + 1e-3 * sc * np.random.normal(size=true_state.Nvars) for _ in range(Nwalkers)])
     nsteps = int(Niter / Nwalkers)
@@ -169,7 +174,7 @@ def run_smala_gpu(label, Niter, true_state, obs, eps, alpha, nchains=1, seed=0):
     """`nchains` independent SMALA chains (Smala.step, mcmc.py:167-187)."""
     from . import _abi
     ctx = _abi.default_context()
-    t0 = datetime.utcnow()
+    t0 = _utcnow()
     r = _sampler_state(true_state)._model(ctx).smala_run(obs._handle(ctx), np.tile(true_state.get_params(), (nchains, 1)),
                                                          eps, alpha, Niter, seed=seed)
     print("Acceptance rate: %.3f%%" % (100. * r["n_accept"].mean() / max(Niter, 1)))
@@ -180,7 +185,7 @@ def run_alsmala_gpu(label, Niter, true_state, obs, eps, alpha, bern_a, bern_b=No
     """`nchains` ALSMALA chains under run_alsmala's schedule exp(-bern_a*i/Niter) (driver.py:171-200; bern_b is unused there)."""
     from . import _abi
     ctx = _abi.default_context()
-    t0 = datetime.utcnow()
+    t0 = _utcnow()
     r = _sampler_state(true_state)._model(ctx).alsmala_run(obs._handle(ctx), np.tile(true_state.get_params(), (nchains, 1)),
                                                            eps, alpha, bern_a, Niter, niter_total=Niter, seed=seed)
     print("Acceptance rate: %.3f%%" % (100. * r["n_accept"].mean() / max(Niter, 1)))

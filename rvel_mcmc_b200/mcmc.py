@@ -6,12 +6,17 @@ stretch move of emcee 2.2.1 (the version the reference ran, script.sh:9) is rest
 ``StretchSampler`` and evaluates each half-ensemble as ONE batched kernel call.
 Fused many-chain device samplers live in ``rvel_mcmc_b200.samplers``.
 """
-from datetime import datetime
+from datetime import datetime, timezone
 
 import numpy as np
 
 from . import _abi
 from ._abi import Encounter
+
+def _utcnow():
+    """Naive UTC timestamp, what the reference's datetime.utcnow() returned (driver.py:64)."""
+    return datetime.now(timezone.utc).replace(tzinfo=None)
+
 
 
 class Mcmc(object):
@@ -36,7 +41,7 @@ def lnprob(x, e):
     try:
         logp = e.state.get_logp(e.obs)
     except Exception:
-        print("Collision! {t}".format(t=datetime.utcnow()))
+        print("Collision! {t}".format(t=_utcnow()))
         return -np.inf
     return logp
 
@@ -125,7 +130,7 @@ def _scale_vector(state, scales):
 
 
 def _collision():
-    print("Collision! {t}".format(t=datetime.utcnow()))
+    print("Collision! {t}".format(t=_utcnow()))
     return False
 
 
