@@ -232,3 +232,18 @@ def test_kat1_initial_conditions_on_gpu(ctx):
     assert sim.N == 3 and abs(sim.particles[0].vx - (-0.00041883056816320016)) < 1e-18
     assert abs(sim.particles[0].vx - s.get_rv([0.0])[0]) < 1e-18
     assert abs(sim.exit_min_distance - 2. * 1.04404207 * (0.00083037971 / 3.) ** (1. / 3.)) < 1e-15
+
+
+def test_rv_of_walker_ball_matches_oracle_to_1e9(ctx):
+    # north_star tolerance for the observable itself: RVs within 1e-9 relative of rebound (here: of the KAT-pinned oracle),
+    # both epoch orders the reference uses (obs.tf forward; obs.tb = first hop to the most negative epoch, then forward)
+    obs = T.load_vels("HD155358.vels")
+    m = _model(ctx, np.zeros((2, 7)), T.FP10, T.FE10, 0.0)
+    theta = T.gaussian_ball(T.HD_SOL, T.HD_SCALE_VEC, 48, 21, width=0.3)
+    for times in (obs.tf, obs.tb):
+        rv, st = m.rv_curve(theta, times)
+        assert (st == 0).all()
+        for w in range(len(theta)):
+            so, ro = T.orc_rv(T.elems_from_planets(T.planets_from_vec(theta[w])), 0.0, times)
+            assert so == 0
+            assert np.abs(rv[w] - ro).max() <= 1e-9 * np.abs(ro).max(), w
