@@ -197,3 +197,27 @@ def test_reference_api_smala_and_alsmala_step_by_step():
     ba, _ = driver.run_alsmala("t", 60, true_state, obs, 1.2, 0.14, 3.0, 0.0, printing_every=1000)
     assert ba.mcmc_chain.shape == (61, 3) and len(np.unique(ba.mcmc_chain[:, 0])) > 10
     assert ba.mcmc.state.logp_d is not None and ba.mcmc.state.logp_dd.shape == (3, 3)
+
+
+def test_device_group_single_process_multi_gpu():
+    """rvel_mcmc_b200.multigpu.DeviceGroup: all visible GPUs from one process (one host thread per GPU); results equal the
+    single-GPU ones bit for bit.  Runs with however many GPUs the box has (1 on the default test box)."""
+    import os
+    from rvel_mcmc_b200 import observations, state, _abi
+    from rvel_mcmc_b200.multigpu import DeviceGroup
+    obs = observations.Observation_FromFile(os.path.join(T.GOLDEN, "HD155358.vels"), Npoints=100)
+    st = state.State(T.planets_from_vec(T.HD_SOL)); st.hillRadiusFactor = 2.
+    g = DeviceGroup()
+    try:
+        theta = T.gaussian_ball(T.HD_SOL, T.HD_SCALE_VEC, 1000, 3)
+        lg, sg = g.loglik(st, obs, theta)
+        ctx = _abi.default_context()
+        l1, s1 = st._model(ctx).loglik(obs._handle(ctx), theta)
+        assert np.array_equal(lg, l1) and np.array_equal(sg, s1)
+        r = g.mh_run(st, obs, theta[:64], np.array(T.HD_SCALE_VEC), 0.1, 8, seed=4, record_accepts=True)
+        r1 = st._model(ctx).mh_run(obs._handle(ctx), theta[:64], np.array(T.HD_SCALE_VEC), 0.1, 8, seed=4, record_accepts=True)
+        assert np.array_equal(r["chain"], r1["chain"]) and np.array_equal(r["accepted"], r1["accepted"])
+        lv, gv, hv, sv = g.loglik_d_dd(st, obs, theta[:16])
+        assert lv.shape == (16,) and gv.shape == (16, 10) and hv.shape == (16, 10, 10) and (sv == 0).all()
+    finally:
+        g.close()
