@@ -33,7 +33,7 @@ def main():
     import torch
     import torch.distributed as dist
     from rvel_mcmc_b200 import _abi, observations, state
-    from rvel_mcmc_b200.samplers import chain_shard, ess
+    from rvel_mcmc_b200.samplers import chain_shard
 
     world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))

@@ -130,7 +130,7 @@ def test_posterior_moments_agree_between_samplers(ctx):
 
 def test_reference_api_samplers_run_on_gpu():
     import os
-    from rvel_mcmc_b200 import observations, state, mcmc, driver
+    from rvel_mcmc_b200 import observations, state, driver
     np.random.seed(12)
     true_state = state.State([{"a": 0.2275, "h": 0., "k": 0., "m": 0.001965}], ignore_vars=["m"])
     obs = observations.FakeObservation(true_state, Npoints=70, error=3.5e-4, errorVar=9e-5, tmax=1.37)

@@ -1,6 +1,5 @@
 """Pins the CPU oracle (oracle/rv_oracle.c) against every golden value the reference holds for the hot
 path.  Runs without a GPU."""
-import ctypes as C
 
 import numpy as np
 

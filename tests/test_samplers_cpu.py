@@ -1,12 +1,10 @@
 """CPU tests of the sampler contract: the oracle's Philox against Random123 known answers, and the multi-rank
 sharding logic of the stretch move (world_size-2 gloo) against the single-rank oracle run."""
 import ctypes as C
-import os
 import socket
 import sys
 
 import numpy as np
-import pytest
 
 import rvtest as T
 
