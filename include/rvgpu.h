@@ -74,7 +74,10 @@ int rv_model_destroy(rv_model* model);
  * "dt0" (1e-3), "epsilon" (1e-9), "max_attempts", "hill_factor", "mapping" (0 lane-per-planet, 1 thread-per-walker),
  * "check_prior" (1; 0 = rv_loglik_d_dd integrates even outside the hard prior, as state.py:290 does),
  * "monotone_backward" (0 = rv_loglik visits obs.tb in its stored order as state.py:91 does; 1 = one sweep from 0 to the
- *   most negative epoch, the order state.py:273 uses: about half the backward steps, logp equal to ~1e-11)            */
+ *   most negative epoch, the order state.py:273 uses: about half the backward steps, logp equal to ~1e-11),
+ * "dense_output" (0 = every hop ends exactly on its epoch, rebound's exact_finish_time = 1; 1 = rv_loglik integrates each
+ *   leg once with natural IAS15 steps and reads the RV at every epoch from the step's acceleration polynomial: the
+ *   number of steps no longer grows with the number of epochs; implies monotone_backward; logp equal to ~1e-10)      */
 int rv_model_set_option(rv_model* model, const char* key, double value);
 
 /* ---- State.get_logp (state.py:103-110) for W parameter vectors; HOST buffers -------------------- */

@@ -218,6 +218,7 @@ int rv_model_set_option(rv_model* m, const char* key, double value) {
     else if (!strcmp(key, "mapping")) m->mapping = (int)value;
     else if (!strcmp(key, "check_prior")) m->h.check_prior = value != 0.0;
     else if (!strcmp(key, "monotone_backward")) m->h.monotone_backward = value != 0.0;
+    else if (!strcmp(key, "dense_output")) m->h.dense_output = value != 0.0;
     else if (!strcmp(key, "integrator")) {
         if (value != 0.0 && value != 1.0) return fail(ctx, -21, "rv_model_set_option: integrator must be 0 (IAS15) or 1 (WHFast)");
         m->h.integrator = (int)value;
@@ -252,7 +253,7 @@ static int loglik_dev_impl(rv_ctx* ctx, const rv_model* model, const rv_obs* obs
     a.part_chi2 = ctx->d_part; a.part_status = ctx->d_pstat;
     a.item_counter = ctx->d_item_counter;
     a.work_counters = ctx->count_work ? ctx->d_work : nullptr;
-    CU(ctx, rv::launch_loglik(a, model->h.P, model->h.D, model->mapping, ctx->num_sms, s));
+    CU(ctx, rv::launch_loglik(a, model->h.P, model->h.D, model->mapping, model->h.dense_output, ctx->num_sms, s));
     CU(ctx, rv::launch_finalize(ctx->d_part, ctx->d_pstat, W, obs->npoints, d_logp, d_status, ctx->d_item_counter, s));
     return 0;
 }
@@ -322,7 +323,7 @@ int rv_rv_curve(rv_ctx* ctx, const rv_model* model, const double* theta, int64_t
     a.part_chi2 = nullptr; a.part_status = ctx->d_pstat;
     a.item_counter = ctx->d_item_counter;
     a.work_counters = ctx->count_work ? ctx->d_work : nullptr;
-    CU(ctx, rv::launch_loglik(a, model->h.P, model->h.D, model->mapping, ctx->num_sms, s));
+    CU(ctx, rv::launch_loglik(a, model->h.P, model->h.D, model->mapping, model->h.dense_output, ctx->num_sms, s));
     CU(ctx, rv::launch_curve_finalize(ctx->d_item_counter, s));
     if (nt) CU(ctx, cudaMemcpyAsync(rv, ctx->d_rv, (size_t)W * nt * sizeof(double), cudaMemcpyDeviceToHost, s));
     CU(ctx, cudaMemcpyAsync(status, ctx->d_pstat, (size_t)W * sizeof(int32_t), cudaMemcpyDeviceToHost, s));

@@ -52,6 +52,10 @@ struct Model {
     int max_attempts;       // safety bound on IAS15 step attempts per leg
     int check_prior;        // variational entry point: test priorHard first (1, default) or integrate regardless (0)
     int integrator;         // 0 = IAS15 (rebound's default, what the reference runs); 1 = WHFast with fixed step dt0
+    int dense_output;       // plain path, 0 (default): every integrate() hop ends exactly on its epoch (rebound's
+                            // exact_finish_time = 1: at least one truncated step per epoch); 1 = one continuous
+                            // integration per leg with natural steps, the star's velocity at each epoch read from
+                            // the step's own acceleration polynomial (implies monotone_backward)
     int monotone_backward;  // plain path: 0 (default) visit obs.tb in stored (ascending) order as state.py:91 does --
                             // first hop to the most negative epoch, then forward; 1 = sweep 0 -> most negative once
                             // (the order state.py:273 uses), half the backward steps, logp equal to ~1e-11
@@ -264,8 +268,8 @@ struct Hist {
 // ---------------------------------------------------------------------------------------------
 // One walker (or one planet of a walker when PL == 1): state, gravity, encounter test, set-up.  The IAS15 step
 // itself is WalkerG::attempt (rv_core_g.cuh).
-// VAR: compile-time tuning switch -- bit1: IAS15 tables read from the constant bank (else folded into immediates;
-// measured faster on B200, profiles/r01c_variants.txt).
+// VAR: compile-time switches -- bit1 (2): IAS15 tables read from the constant bank (else folded into immediates; measured
+// identical on B200, profiles/r01c_variants.txt); bit2 (4): dense-output instantiation (model option dense_output).
 template <int VAR> RV_D double tH(int n) { if constexpr ((VAR & 2) != 0) return rvtabm::H[n]; else return rvtab::H[n]; }
 template <int VAR> RV_D double tGA(int n) { if constexpr ((VAR & 2) != 0) return rvtabm::GA[n]; else return rvtab::GA[n]; }
 template <int VAR> RV_D double tPRED(int n, int k) { if constexpr ((VAR & 2) != 0) return rvtabm::PRED[n][k]; else return rvtab::PRED[n][k]; }

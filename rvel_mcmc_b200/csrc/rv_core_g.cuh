@@ -19,6 +19,10 @@ struct WalkerG : Walker<P, D, PL, VAR> {
     using B = Walker<P, D, PL, VAR>;
     static constexpr int NC = B::NC;
     static constexpr int HIST = 21;   // doubles of shared-memory history per coordinate: er[7], br[7], e[7]
+    static constexpr int DENSE0 = HIST * NC;               // then 9 per own planet: v0x, a0x, b0x..b6x of the last step
+    static constexpr bool kDense = (VAR & 4) != 0;         // dense-output instantiation (model option dense_output)
+    static constexpr int LANE_DOUBLES = HIST * NC + (kDense ? 9 * PL : 0);   // shared-memory doubles per lane
+    using B::mu;
     using B::x0; using B::v0; using B::a0; using B::ha0; using B::csx; using B::csv;
     using B::b;                       // holds b between attempts and g inside the predictor-corrector loop
     using B::t; using B::dt; using B::dt_last_done; using B::grp; using B::hist; using B::epsilon;
@@ -58,6 +62,26 @@ struct WalkerG : Walker<P, D, PL, VAR> {
             }
             b[n - 1][c] = sel(commit, gn, b[n - 1][c]);
         }
+    }
+
+    // Star x-velocity at fraction h in (0, 1] of the step just accepted (size dt_done), from that step's acceleration
+    // polynomial a(h) = a0 + b0 h + ... + b6 h^7:  v(h) = v0 + dt h (a0 + h (b0/2 + h (b1/3 + ... + h b6/8))).
+    RV_D double dense_star_vx(double h, double dt_done) const {
+        double s = 0.0;
+#pragma unroll
+        for (int pl = 0; pl < PL; pl++) {
+            double p = hist.at(DENSE0 + 9 * pl + 8) * (1. / 8.);
+            p = fma(p, h, hist.at(DENSE0 + 9 * pl + 7) * (1. / 7.));
+            p = fma(p, h, hist.at(DENSE0 + 9 * pl + 6) * (1. / 6.));
+            p = fma(p, h, hist.at(DENSE0 + 9 * pl + 5) * (1. / 5.));
+            p = fma(p, h, hist.at(DENSE0 + 9 * pl + 4) * (1. / 4.));
+            p = fma(p, h, hist.at(DENSE0 + 9 * pl + 3) * (1. / 3.));
+            p = fma(p, h, hist.at(DENSE0 + 9 * pl + 2) * 0.5);
+            p = fma(p, h, hist.at(DENSE0 + 9 * pl + 1));
+            const double vx = fma(dt_done * h, p, hist.at(DENSE0 + 9 * pl + 0));
+            s += mu[pl] * vx;
+        }
+        return -grp.template sum<false>(s);
     }
 
     RV_D void predict_g(double q, const double (&_e)[7], const double (&_b)[7], int c) {
@@ -205,6 +229,15 @@ struct WalkerG : Walker<P, D, PL, VAR> {
                 if (fabs(dt_new) > 4.0 * fabs(dt_done)) dt_new = dt_done * 4.0;      // same sign: dt_new/dt_done > 1/safety
                 dt = dt_new;
                 const double dt2 = dt_done * dt_done;
+                if constexpr (kDense) {
+#pragma unroll
+                    for (int pl = 0; pl < PL; pl++) {
+                        hist.at(DENSE0 + 9 * pl + 0) = v0[pl * D];
+                        hist.at(DENSE0 + 9 * pl + 1) = a0[pl * D];
+#pragma unroll
+                        for (int k = 0; k < 7; k++) hist.at(DENSE0 + 9 * pl + 2 + k) = b[k][pl * D];
+                    }
+                }
 #pragma unroll
                 for (int c = 0; c < NC; c++) {
                     {

@@ -78,8 +78,8 @@ static cudaError_t launch_one(const LoglikArgs& a, int num_sms, cudaStream_t str
     auto kern = loglik_kernel<P, D, PL, NT, MINB, VAR>;
     const int nobs = a.nf + a.nb;
     constexpr int NC = PL * D;
-    constexpr int W21 = WalkerG<P, D, PL, VAR>::HIST;
-    const size_t smem_hist = sizeof(double) * (size_t)W21 * NC * NT;
+    constexpr int LANE_DOUBLES = WalkerG<P, D, PL, VAR>::LANE_DOUBLES;
+    const size_t smem_hist = sizeof(double) * (size_t)LANE_DOUBLES * NT;
     const size_t smem_obs = sizeof(double) * (size_t)3 * nobs;
     LoglikArgs args = a;
     // stage the observations only while MINB CTAs still fit in the SM's 227 KB of shared memory
@@ -102,20 +102,26 @@ static cudaError_t launch_one(const LoglikArgs& a, int num_sms, cudaStream_t str
     return cudaGetLastError();
 }
 
-// mapping: 0 = one lane per planet (default), 1 = one thread per walker
-cudaError_t launch_loglik(const LoglikArgs& a, int P, int D, int mapping, int num_sms, cudaStream_t stream) {
+// mapping: 0 = one lane per planet (default), 1 = one thread per walker; dense: the dense-output instantiations
+template <int VAR>
+static cudaError_t launch_loglik_var(const LoglikArgs& a, int P, int D, int mapping, int num_sms, cudaStream_t stream) {
     const int key = P * 100 + D * 10 + mapping;
     switch (key) {
-        case 120: case 121: return launch_one<1, 2, 1, 128, 3>(a, num_sms, stream);
-        case 130: case 131: return launch_one<1, 3, 1, 128, 2>(a, num_sms, stream);
-        case 220: return launch_one<2, 2, 1, 128, 3>(a, num_sms, stream);
-        case 221: return launch_one<2, 2, 2, 128, 2>(a, num_sms, stream);
-        case 230: return launch_one<2, 3, 1, 128, 2>(a, num_sms, stream);
-        case 231: return launch_one<2, 3, 1, 128, 2>(a, num_sms, stream);
-        case 320: case 321: return launch_one<3, 2, 1, 128, 3>(a, num_sms, stream);
-        case 330: case 331: return launch_one<3, 3, 1, 128, 2>(a, num_sms, stream);
+        case 120: case 121: return launch_one<1, 2, 1, 128, 3, VAR>(a, num_sms, stream);
+        case 130: case 131: return launch_one<1, 3, 1, 128, 2, VAR>(a, num_sms, stream);
+        case 220: return launch_one<2, 2, 1, 128, 3, VAR>(a, num_sms, stream);
+        case 221: return launch_one<2, 2, 2, 128, 2, VAR>(a, num_sms, stream);
+        case 230: return launch_one<2, 3, 1, 128, 2, VAR>(a, num_sms, stream);
+        case 231: return launch_one<2, 3, 1, 128, 2, VAR>(a, num_sms, stream);
+        case 320: case 321: return launch_one<3, 2, 1, 128, 3, VAR>(a, num_sms, stream);
+        case 330: case 331: return launch_one<3, 3, 1, 128, 2, VAR>(a, num_sms, stream);
         default: return cudaErrorInvalidValue;
     }
+}
+
+cudaError_t launch_loglik(const LoglikArgs& a, int P, int D, int mapping, int dense, int num_sms, cudaStream_t stream) {
+    if (dense && !a.times) return launch_loglik_var<4>(a, P, D, mapping, num_sms, stream);
+    return launch_loglik_var<0>(a, P, D, mapping, num_sms, stream);
 }
 
 cudaError_t launch_finalize(const double* part_chi2, const int* part_status, long long W, double npoints,

@@ -42,7 +42,9 @@ RV_D void run_items(WK& w, const LoglikArgs& a, const double* st, const double* 
     const int max_attempts = a.model->max_attempts;
     const int nvars = a.model->nvars;
     const bool leader = (w.grp.rank == 0);
-    const bool mono = a.model->monotone_backward != 0;
+    const bool dense_mode = WK::kDense && !curve;       // the launcher picks the dense instantiation from the model option
+    const bool mono = a.model->monotone_backward != 0 || dense_mode;
+    double sgn = 1.0;       // dense output: direction of the leg's single integration
     bool rev = false;       // this item visits its epochs in reversed storage order
     int phase = lane_active ? PH_NEED_ITEM : PH_DONE;
     long long item = -1, wi = 0;
@@ -83,6 +85,26 @@ RV_D void run_items(WK& w, const LoglikArgs& a, const double* st, const double* 
                 const int s = w.setup(a.model, a.theta + wi * nvars, !curve);
                 if (s != ST_OK) { finish(s); continue; }
                 phase = PH_ENTRY;
+                if (dense_mode) {
+                    // one integration per leg: natural steps away from t = 0, RVs read inside the steps
+                    sgn = (item < a.W) ? -1.0 : 1.0;
+                    w.dt = sgn * fabs(w.dt);
+                    if (w.template encounter<false>()) { finish(ST_ENCOUNTER); continue; }
+                    int st0 = ST_OK;
+                    while (c.ie < c.n) {            // epochs at the start time itself (obs.tf[0] = 0, obs.tb[-1] = 0)
+                        const int io = rev ? c.n - 1 - c.ie : c.ie;
+                        const double d = (lt[io] - w.t) * sgn;
+                        if (d > 0.0) break;
+                        if (d < 0.0) { st0 = ST_NONFINITE; break; }       // an epoch behind the start: not a monotone leg
+                        const double vx = w.star_vx();
+                        const double r = vx - lrv[io], er = lerr[io];
+                        c.chi2 += (r * r) / (er * er);
+                        c.ie++;
+                    }
+                    if (st0 != ST_OK || c.ie == c.n) { finish(st0); continue; }
+                    phase = PH_STEP;
+                    break;
+                }
             }
             if (phase == PH_ENTRY) {            // sim.integrate(t) entry (rebound: reb_integrate)
                 if (c.ie == c.n) { finish(ST_OK); continue; }
@@ -119,6 +141,22 @@ RV_D void run_items(WK& w, const LoglikArgs& a, const double* st, const double* 
             c.attempts++;
             if (c.attempts > max_attempts || !isfinite(w.dt) || w.dt == 0.0) {
                 finish(ST_NONFINITE);
+            } else if ((r & 1) && dense_mode) {
+                // epochs inside the step just accepted: (t - dt_done, t]
+                const double dt_done = w.dt_last_done;
+                int st1 = (r & 2) ? ST_ENCOUNTER : ST_OK;
+                while (st1 == ST_OK && c.ie < c.n) {
+                    const int io = rev ? c.n - 1 - c.ie : c.ie;
+                    if ((lt[io] - w.t) * sgn > 0.0) break;
+                    const double h = 1.0 + (lt[io] - w.t) / dt_done;
+                    double vx = 0.0;
+                    if constexpr (WK::kDense) vx = w.dense_star_vx(h, dt_done);
+                    if (!isfinite(vx)) { st1 = ST_NONFINITE; break; }
+                    const double rr = vx - lrv[io], er = lerr[io];
+                    c.chi2 += (rr * rr) / (er * er);
+                    c.ie++;
+                }
+                if (st1 != ST_OK || c.ie == c.n) finish(st1);
             } else if (r & 1) {
                 if (r & 2) c.status = ST_ENCOUNTER;
                 phase = PH_CHECK;

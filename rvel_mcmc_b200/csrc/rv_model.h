@@ -41,6 +41,7 @@ inline int build_model(Model* m, int P, const double* fixed, int nvars, const in
     m->max_attempts = 1 << 20;
     m->check_prior = 1;
     m->monotone_backward = 0;
+    m->dense_output = 0;
     m->integrator = 0;
     return 0;
 }

@@ -20,7 +20,7 @@ template <class WK, int NCOORD>
 void run_with(const rv::LoglikArgs& a) {
     WK w;
     w.grp.init(0);
-    std::vector<double> hist(21 * NCOORD, 0.0);
+    std::vector<double> hist(WK::LANE_DOUBLES, 0.0);
     w.hist.p = hist.data(); w.hist.stride = 1;
     HostFetch f{a.item_counter};
     HostAll all;
@@ -29,12 +29,14 @@ void run_with(const rv::LoglikArgs& a) {
 
 template <int P, int D>
 void run(const rv::LoglikArgs& a) {
-    run_with<rv::WalkerG<P, D, P, 0>, P * D>(a);
+    if (a.model->dense_output) run_with<rv::WalkerG<P, D, P, 4>, P * D>(a);
+    else run_with<rv::WalkerG<P, D, P, 0>, P * D>(a);
 }
 }  // namespace
 
-static int g_monotone = 0;
+static int g_monotone = 0, g_dense = 0;
 extern "C" void mirror_set_monotone(int v) { g_monotone = v; }
+extern "C" void mirror_set_dense(int v) { g_dense = v; }
 
 extern "C" int mirror_loglik(int P, const double* fixed, int nvars, const int* fp, const int* fe, double hill, int dims,
                              const double* tf, const double* rvf, const double* ef, int nf,
@@ -45,6 +47,7 @@ extern "C" int mirror_loglik(int P, const double* fixed, int nvars, const int* f
     int rc = rv::build_model(&m, P, fixed, nvars, fp, fe, hill, dims);
     if (rc) return rc;
     m.monotone_backward = g_monotone;
+    m.dense_output = g_dense;
     std::vector<double> ot(nf + nb), orv(nf + nb), oerr(nf + nb);
     for (int i = 0; i < nf; i++) { ot[i] = tf[i]; orv[i] = rvf[i]; oerr[i] = ef[i]; }
     for (int i = 0; i < nb; i++) { ot[nf + i] = tb[i]; orv[nf + i] = rvb[i]; oerr[nf + i] = eb[i]; }

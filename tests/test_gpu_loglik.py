@@ -247,3 +247,31 @@ def test_rv_of_walker_ball_matches_oracle_to_1e9(ctx):
             so, ro = T.orc_rv(T.elems_from_planets(T.planets_from_vec(theta[w])), 0.0, times)
             assert so == 0
             assert np.abs(rv[w] - ro).max() <= 1e-9 * np.abs(ro).max(), w
+
+
+def test_dense_output_option_matches_default(ctx):
+    # model option: one continuous integration per leg, RVs from the step polynomial (not the default: the default keeps
+    # rebound's exact-finish-time step sequence)
+    obs = T.load_vels("HD155358.vels")
+    oh = _obs_handle(ctx, obs)
+    m = _model(ctx, np.zeros((2, 7)), T.FP10, T.FE10, 2.0)
+    theta = T.gaussian_ball(T.HD_SOL, T.HD_SCALE_VEC, 4096, 78)
+    theta[0] = T.HD_SOL
+    for k in range(3):
+        theta[1 + k] = T.KAT5[k][0]
+    ctx.count_work(True); ctx.work_counters(reset=True)
+    l0, s0 = m.loglik(oh, theta)
+    c0 = ctx.work_counters(reset=True)
+    m.set_option("dense_output", 1)
+    l1, s1 = m.loglik(oh, theta)
+    c1 = ctx.work_counters(reset=True)
+    ctx.count_work(False)
+    assert np.array_equal(s0, s1) and list(s1[1:4]) == [3, 3, 3]
+    ok = s0 == 0
+    assert np.abs(l1[ok] - l0[ok]).max() < 1e-8 and abs(l1[0] - T.KAT2_LOGP) < 5e-11
+    assert c1[1] < 0.7 * c0[1] and c1[0] < 0.7 * c0[0]
+    for mapping in (1,):                      # thread-per-walker mapping keeps its own per-planet dense data
+        m2 = _model(ctx, np.zeros((2, 7)), T.FP10, T.FE10, 2.0, mapping=mapping)
+        m2.set_option("dense_output", 1)
+        l2, s2 = m2.loglik(oh, theta[:256])
+        assert np.array_equal(s2, s1[:256]) and np.abs(l2[ok[:256]] - l1[:256][ok[:256]]).max() < 1e-8

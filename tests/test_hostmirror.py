@@ -111,3 +111,29 @@ def test_mirror_massive_planets_star_in_norm():
     lm2, gm, hm, sm2, _ = T.mirror_loglik_d_dd(E, fp, fe, 0.0, obs, theta)
     assert (sm2 == 0).all() and np.abs(lm2 - lo2).max() < 1e-9 * np.abs(lo2).max()
     assert np.abs(gm - go).max() < 1e-8 * np.abs(go).max() and np.abs(hm - ho).max() < 1e-8 * np.abs(ho).max()
+
+
+def test_mirror_dense_output_option():
+    # natural IAS15 steps + RVs read from the step's acceleration polynomial instead of a truncated step per epoch:
+    # same likelihood (north_star: 1e-6 absolute), step count independent of the number of epochs
+    obs, theta = _hd(6, 9)
+    lo, so, _ = T.orc_logp_batch(np.zeros((2, 7)), T.FP10, T.FE10, 2.0, obs, theta)
+    l0, s0, c0 = T.mirror_loglik(np.zeros((2, 7)), T.FP10, T.FE10, 2.0, obs, theta)
+    T.mirror().mirror_set_dense(1)
+    try:
+        l1, s1, c1 = T.mirror_loglik(np.zeros((2, 7)), T.FP10, T.FE10, 2.0, obs, theta)
+        rng = np.random.RandomState(2)
+        o = T.Obs()
+        o.tf = np.concatenate([[0.0], np.sort(rng.uniform(0, 30, 500))]); o.tb = np.sort(rng.uniform(-30, 0, 500))
+        o.rvf = 1e-4 * rng.normal(size=501); o.rvb = 1e-4 * rng.normal(size=500)
+        o.errorf = np.full(501, 2e-4); o.errorb = np.full(500, 2e-4); o.Npoints = 1000
+        l2, s2, c2 = T.mirror_loglik(np.zeros((2, 7)), T.FP10, T.FE10, 2.0, o, theta[:2])
+        # encounter vectors still flag, whatever the epoch handling (KAT-5)
+        l3, s3, _ = T.mirror_loglik(np.zeros((2, 7)), T.FP10, T.FE10, 2.0, obs, np.array([k[0] for k in T.KAT5]))
+    finally:
+        T.mirror().mirror_set_dense(0)
+    lo2, so2, co2 = T.orc_logp_batch(np.zeros((2, 7)), T.FP10, T.FE10, 2.0, o, theta[:2])
+    assert np.array_equal(s1, so) and (s1 == 0).all() and np.abs(l1 - lo).max() < 1e-9
+    assert c1[1] < 0.7 * c0[1]
+    assert (s2 == 0).all() and np.abs(l2 - lo2).max() < 1e-9 * np.abs(lo2).max() and c2[1] < 0.6 * co2[1]
+    assert list(s3) == [3, 3, 3]

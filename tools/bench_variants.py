@@ -34,6 +34,19 @@ for mp in [int(x) for x in sys.argv[1:]] or [0]:
     if ref is None: ref = lp.copy()
     print("mapping %2d: %.2f ms  %.3f Mevals/s  max|dlogp vs first|=%.2e" % (mp, best, W / best / 1e3, np.abs(lp - ref).max()))
 
+# non-default epoch handling: monotone backward sweep, dense output
+for key in ("monotone_backward", "dense_output"):
+    m.set_option("mapping", 0); m.set_option(key, 1)
+    m.loglik_dev(oh, theta.data_ptr(), W, logp.data_ptr(), st.data_ptr(), s); torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); m.loglik_dev(oh, theta.data_ptr(), W, logp.data_ptr(), st.data_ptr(), s); e1.record()
+        torch.cuda.synchronize(); best = min(best, e0.elapsed_time(e1))
+    lp = logp.cpu().numpy()
+    print("%s=1: %.2f ms  %.3f Mevals/s  max|dlogp vs default|=%.2e" % (key, best, W / best / 1e3, np.abs(lp - ref).max() if ref is not None else -1))
+    m.set_option(key, 0)
+
 # optional WHFast variant, dt = P_inner/20 (BASELINE configs[4])
 m.set_option("mapping", 0)
 for dt_div in (20, 50):
