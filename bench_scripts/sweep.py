@@ -183,6 +183,17 @@ def main():
                       "ms": 1e3 * sec, "evals_per_s": W / sec, "ok_fraction": float(okb.float().mean().item()),
                       "max_abs_dlogp_vs_ias15": float((lp[okb] - ref[okb]).abs().max().item())})
                 m.set_option("integrator", 0); m.set_option("dt0", 1e-3)
+                # IAS15 with the non-default dense_output option (natural steps, RVs read inside the steps)
+                m.set_option("dense_output", 1)
+                m.loglik_dev(oh, th.data_ptr(), min(hi - lo, 1024), lp.data_ptr(), stt.data_ptr(), s); torch.cuda.synchronize()
+                e0.record(); m.loglik_dev(oh, th.data_ptr(), hi - lo, lp.data_ptr(), stt.data_ptr(), s); e1.record()
+                torch.cuda.synchronize()
+                sec = maxsec(e0.elapsed_time(e1) * 1e-3)
+                okb = stt == 0
+                emit({"config": "C5 sweep, HD155358-shape truth, IAS15 dense_output=1", "walkers": W, "epochs": nep + 1,
+                      "ms": 1e3 * sec, "evals_per_s": W / sec, "ok_fraction": float(okb.float().mean().item()),
+                      "max_abs_dlogp_vs_default": float((lp[okb] - ref[okb]).abs().max().item())})
+                m.set_option("dense_output", 0)
     if world > 1:
         dist.barrier(); dist.destroy_process_group()
 
