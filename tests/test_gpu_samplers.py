@@ -168,7 +168,7 @@ def test_fused_device_drivers_agree_with_each_other():
     obs = observations.FakeObservation(true_state, Npoints=70, error=3.5e-4, errorVar=9e-5, tmax=1.37)   # (Ex)Full Test notebook
     scal = {'a': 3e-4, 'h': 0.01, 'k': 0.01}
     bm, _ = driver.run_mh_gpu("t", 1200, true_state, obs, scal, 5, nchains=64, seed=1)
-    be, _ = driver.run_emcee_gpu("t", 64 * 600, true_state, obs, 64, scal, seed=2)
+    be, _ = driver.run_emcee_gpu("t", 64 * 600, true_state, obs, 64, scal, seed=2, fast=True)      # dense-output likelihood
     bs, _ = driver.run_smala_gpu("t", 300, true_state, obs, 1.2, 0.14, nchains=64, seed=3)
     ba, _ = driver.run_alsmala_gpu("t", 300, true_state, obs, 1.2, 0.14, 3.0, nchains=64, seed=4)
     assert bm.mcmc_chain.shape == (64 * 1200, 3) and be.mcmc_chain.shape == (64 * 600, 3) and bs.mcmc_chain.shape == (64 * 300, 3)
