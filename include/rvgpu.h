@@ -162,6 +162,15 @@ int rv_alsmala_run(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, double
                    uint32_t first_step, int nsteps, int thin, int64_t W, double* chain, double* chain_logp,
                    uint64_t* n_accept, uint8_t* accepted, int32_t* status, uint8_t* full_step);
 
+/* ---- device buffers for callers without a GPU array library (single-process multi-GPU: multigpu.DeviceGroup) ---- */
+/* Plain device allocations on the context's GPU and synchronous copies; rv_dev_copy_peer copies between two contexts'
+ * GPUs (cudaMemcpyPeer: NVLink peer-to-peer where the driver allows it, staged through the host otherwise).       */
+int rv_dev_alloc(rv_ctx* ctx, int64_t nbytes, void** out);
+int rv_dev_free(rv_ctx* ctx, void* p);
+int rv_dev_upload(rv_ctx* ctx, void* dst_dev, const void* src_host, int64_t nbytes);
+int rv_dev_download(rv_ctx* ctx, void* dst_host, const void* src_dev, int64_t nbytes);
+int rv_dev_copy_peer(rv_ctx* dst_ctx, void* dst_dev, rv_ctx* src_ctx, const void* src_dev, int64_t nbytes);
+
 /* ---- work accounting: force evaluations and IAS15 step attempts since the last reset ----------- */
 int rv_work_counters(rv_ctx* ctx, uint64_t out[2], int reset);
 int rv_count_work(rv_ctx* ctx, int enable);     /* off by default (atomics per item when on)       */

@@ -70,6 +70,11 @@ _SIGNATURES = {
                                       C.c_void_p, C.c_void_p, C.c_void_p]),
     "rv_mh_steps_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
                                   C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]),
+    "rv_dev_alloc": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_void_p)]),
+    "rv_dev_free": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "rv_dev_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
+    "rv_dev_download": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
+    "rv_dev_copy_peer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
     "rv_work_counters": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.c_int]),
     "rv_count_work": (C.c_int, [C.c_void_p, C.c_int]),
     "rv_fp64_peak": (C.c_int, [C.c_void_p, _dp]),
@@ -150,6 +155,27 @@ class Context(object):
 
     def sync(self):
         self.check(self.lib.rv_sync(self.h), "rv_sync")
+
+    # ---- plain device buffers (addresses as ints) ----
+    def dev_alloc(self, nbytes):
+        p = C.c_void_p()
+        self.check(self.lib.rv_dev_alloc(self.h, int(nbytes), C.byref(p)), "rv_dev_alloc")
+        return p.value or 0
+
+    def dev_free(self, addr):
+        self.check(self.lib.rv_dev_free(self.h, C.c_void_p(addr)), "rv_dev_free")
+
+    def dev_upload(self, addr, array):
+        a = np.ascontiguousarray(array)
+        self.check(self.lib.rv_dev_upload(self.h, C.c_void_p(addr), _ptr(a), a.nbytes), "rv_dev_upload")
+
+    def dev_download(self, array, addr):
+        assert array.flags["C_CONTIGUOUS"]
+        self.check(self.lib.rv_dev_download(self.h, _ptr(array), C.c_void_p(addr), array.nbytes), "rv_dev_download")
+
+    def dev_copy_to(self, dst_ctx, dst_addr, src_addr, nbytes):
+        self.check(self.lib.rv_dev_copy_peer(dst_ctx.h, C.c_void_p(dst_addr), self.h, C.c_void_p(src_addr), int(nbytes)),
+                   "rv_dev_copy_peer")
 
     def close(self):
         if getattr(self, "h", None):

@@ -676,6 +676,44 @@ int rv_alsmala_run(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, double
                       thin, W, chain, chain_logp, n_accept, accepted, status, full_step);
 }
 
+int rv_dev_alloc(rv_ctx* ctx, int64_t nbytes, void** out) {
+    if (!ctx || !out || nbytes < 0) return fail(ctx, -1, "rv_dev_alloc: bad argument");
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaMalloc(out, (size_t)(nbytes > 0 ? nbytes : 1)));
+    return 0;
+}
+
+int rv_dev_free(rv_ctx* ctx, void* p) {
+    if (!ctx) return -1;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaFree(p));
+    return 0;
+}
+
+int rv_dev_upload(rv_ctx* ctx, void* dst_dev, const void* src_host, int64_t nbytes) {
+    if (!ctx || (nbytes > 0 && (!dst_dev || !src_host))) return fail(ctx, -1, "rv_dev_upload: bad argument");
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaMemcpyAsync(dst_dev, src_host, (size_t)nbytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int rv_dev_download(rv_ctx* ctx, void* dst_host, const void* src_dev, int64_t nbytes) {
+    if (!ctx || (nbytes > 0 && (!dst_host || !src_dev))) return fail(ctx, -1, "rv_dev_download: bad argument");
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaMemcpyAsync(dst_host, src_dev, (size_t)nbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int rv_dev_copy_peer(rv_ctx* dst_ctx, void* dst_dev, rv_ctx* src_ctx, const void* src_dev, int64_t nbytes) {
+    if (!dst_ctx || !src_ctx || (nbytes > 0 && (!dst_dev || !src_dev))) return fail(src_ctx, -1, "rv_dev_copy_peer: bad argument");
+    CU(src_ctx, cudaSetDevice(src_ctx->device));
+    CU(src_ctx, cudaMemcpyPeerAsync(dst_dev, dst_ctx->device, src_dev, src_ctx->device, (size_t)nbytes, src_ctx->stream));
+    CU(src_ctx, cudaStreamSynchronize(src_ctx->stream));
+    return 0;
+}
+
 int rv_count_work(rv_ctx* ctx, int enable) {
     if (!ctx) return -1;
     ctx->count_work = enable ? 1 : 0;

@@ -219,5 +219,11 @@ def test_device_group_single_process_multi_gpu():
         assert np.array_equal(r["chain"], r1["chain"]) and np.array_equal(r["accepted"], r1["accepted"])
         lv, gv, hv, sv = g.loglik_d_dd(st, obs, theta[:16])
         assert lv.shape == (16,) and gv.shape == (16, 10) and hv.shape == (16, 10, 10) and (sv == 0).all()
+        # the stretch ensemble: slices moved on their own GPUs, exchanged by peer copies
+        W = 64 * len(g)
+        e = g.stretch_run(st, obs, theta[:W], 5, seed=6)
+        e1 = st._model(ctx).stretch_run(obs._handle(ctx), theta[:W], 5, seed=6, record_chain=False)
+        assert np.array_equal(e["theta"], e1["theta"]) and np.array_equal(e["lnp"], e1["lnp"])
+        assert np.array_equal(e["n_accept"], e1["n_accept"])
     finally:
         g.close()
