@@ -109,12 +109,16 @@ static void stretch_half(const prob_t *pq, double *S, long nS, uint64_t id0, con
         uint32_t r[4], rj[4];
         orc_philox(seed, id0 + (uint64_t)i, step, RNG_STRETCH_Z + half, r);
         orc_philox(seed, id0 + (uint64_t)i, step, RNG_STRETCH_J + half, rj);
-        const double t = (a - 1.0) * u53(r[0], r[1]) + 1.0;
-        zz[i] = t * t / a;
+        /* fixed sequence of correctly-rounded operations -- the RNG contract includes the proposal arithmetic, so that
+         * walker positions are bit-identical functions of the accept/reject history on every implementation */
+        const double t = fma(a - 1.0, u53(r[0], r[1]), 1.0);
+        const double tt = t * t;
+        zz[i] = tt / a;
         const long j = (long)(((uint64_t)rj[0] * (uint64_t)nC) >> 32);
         for (int v = 0; v < nvars; v++) {
             const double c = C[j * nvars + v];
-            q[i * nvars + v] = c - zz[i] * (c - S[i * nvars + v]);
+            const double cs = c - S[i * nvars + v];
+            q[i * nvars + v] = fma(-zz[i], cs, c);
         }
         qlp[i] = eval_lnprob(pq, q + i * nvars, NULL);
     }

@@ -4,6 +4,7 @@
 //   MH       (mcmc.py:89-121)  theta' = theta + step_size*scales*z ; accept iff exp(logp'-logp) > u
 //   stretch  (emcee 2.2.1 EnsembleSampler._propose_stretch, driven from mcmc.py:57-65)
 //            zz = ((a-1)u+1)^2/a ; q = c_j - zz (c_j - s) ; accept iff (dim-1) ln zz + lnp(q) - lnp(s) > ln u'
+//            (proposal arithmetic: fixed fma sequence shared bit-for-bit with the oracle)
 #include <cuda_runtime.h>
 #include "rv_launch.h"
 #include "rv_rng.cuh"
@@ -64,12 +65,16 @@ __global__ void stretch_propose_kernel(const double* __restrict__ S, const doubl
     const U4 r = philox4x32_10(seed, id, step, RNG_STRETCH_Z + half);
     const U4 rj = philox4x32_10(seed, id, step, RNG_STRETCH_J + half);
     const double u = u53(r.x, r.y);
-    const double t = (a - 1.0) * u + 1.0;
-    const double zz = t * t / a;
+    // The proposal is written as an explicit sequence of correctly-rounded operations (fma / mul / div / sub), the
+    // same one the CPU oracle executes (oracle/rv_samplers.c), so positions are bit-identical functions of the
+    // accept/reject history: a likelihood that differs by rounding can then only change a decision when
+    // |lnpdiff - ln u| < ~1e-11, instead of seeding an error that the stretch map amplifies (E[ln zz] > 0).
+    const double t = fma(a - 1.0, u, 1.0);
+    const double zz = __ddiv_rn(__dmul_rn(t, t), a);
     const long long j = (long long)(((unsigned long long)rj.x * (unsigned long long)nC) >> 32);
     for (int v = 0; v < nvars; v++) {
         const double c = C[j * nvars + v];
-        q[i * nvars + v] = c - zz * (c - S[i * nvars + v]);
+        q[i * nvars + v] = fma(-zz, __dsub_rn(c, S[i * nvars + v]), c);
     }
     zz_out[i] = zz;
 }

@@ -282,3 +282,31 @@ def mirror_whfast(fixed, fp, fe, hill, dt0, obs, theta, dims=0, times=None):
     if times is not None:
         return rv, status, list(cnt)
     return logp, status, list(cnt)
+
+
+# ---- BASELINE configs[3] ("C4"): synthetic 3-planet near-resonant system -------------------------------
+# the 2:1 pair of mcmc_benchmark_smala.py:32 plus a third planet near the next 2:1; scales / step of mcmc_benchmark_mh.py:52-53
+C4_PLANETS = [{"m": 0.92e-3, "a": 0.2275, "h": -0.06, "k": 0.015, "l": -1.0},
+              {"m": 1.95e-3, "a": 0.3665, "h": 0.02, "k": 0.0, "l": 2.1},
+              {"m": 1.0e-3, "a": 0.59, "h": 0.0, "k": 0.03, "l": 0.7}]
+C4_SCALES = {"m": 1e-3, "a": 0.3, "h": 0.5, "k": 0.5, "l": np.pi / 2}
+FP15 = [p for p in range(3) for _ in range(5)]
+FE15 = [1, 2, 3, 0, 4] * 3                      # a, h, k, m, l per planet (reference parameter order)
+
+
+def c4_problem(nper=40, tmax=30.0, seed=17, err=1.5e-4):
+    """(obs, fixed[3][7], center[15], scale_vec[15]): RVs of the true system from the oracle plus Gaussian noise."""
+    rng = np.random.RandomState(seed)
+    obs = Obs()
+    obs.tf = np.append([0.0], np.sort(rng.uniform(0, tmax / 2, nper)))
+    obs.tb = np.sort(rng.uniform(-tmax / 2, 0, nper))
+    E = elems_from_planets(C4_PLANETS)
+    st, rvf = orc_rv(E, 0.0, obs.tf)
+    st2, rvb = orc_rv(E, 0.0, obs.tb)
+    assert st == 0 and st2 == 0
+    obs.errorf = np.full(nper + 1, err); obs.errorb = np.full(nper, err)
+    obs.rvf = rvf + err * rng.normal(size=nper + 1); obs.rvb = rvb + err * rng.normal(size=nper)
+    obs.Npoints = 2 * nper
+    center = np.array([[p[k] for k in ("a", "h", "k", "m", "l")] for p in C4_PLANETS]).reshape(-1)
+    scale_vec = np.array([C4_SCALES[k] for k in ("a", "h", "k", "m", "l")] * 3)
+    return obs, np.zeros((3, 7)), center, scale_vec
