@@ -26,6 +26,10 @@
 extern "C" {
 #endif
 
+/* Threading: an rv_ctx owns grow-only scratch buffers and a work-queue counter that every entry point (the host-buffer
+ * calls and the *_dev(stream) calls alike) reuses, so a context carries ONE call chain at a time: use it from one host
+ * thread, and give all *_dev calls on one context the same stream (or synchronise between streams).  Concurrent work
+ * = one context per host thread / rank / GPU; contexts are cheap.                                                 */
 typedef struct rv_ctx rv_ctx;     /* one GPU + stream + scratch; one per host thread / rank       */
 typedef struct rv_obs rv_obs;     /* observation set resident in HBM (observations.py:6-16)        */
 typedef struct rv_model rv_model; /* parameter schema resident in HBM (state.py:8-31)              */
@@ -72,7 +76,8 @@ int rv_model_destroy(rv_model* model);
 /* options: "integrator" (0 = IAS15, rebound's default and what the reference runs; 1 = WHFast, fixed step "dt0", each leg
  *   swept monotonically -- no reference call site, parity unpinned; rv_loglik_d_dd / rv_smala_run refuse it),
  * "dt0" (1e-3), "epsilon" (1e-9), "max_attempts", "hill_factor", "mapping" (0 lane-per-planet, 1 thread-per-walker),
- * "check_prior" (1; 0 = rv_loglik_d_dd integrates even outside the hard prior, as state.py:290 does),
+ * "check_prior" (1; 0 = rv_loglik_d_dd / rv_loglik_d_dd_dev integrate even outside the hard prior, as state.py:290
+ *   does; the samplers ignore it and always test the prior; prefer rv_loglik_d_dd_opt's per-call argument),
  * "monotone_backward" (0 = rv_loglik visits obs.tb in its stored order as state.py:91 does; 1 = one sweep from 0 to the
  *   most negative epoch, the order state.py:273 uses: about half the backward steps, logp equal to ~1e-11),
  * "dense_output" (0 = every hop ends exactly on its epoch, rebound's exact_finish_time = 1; 1 = rv_loglik integrates each
@@ -107,6 +112,11 @@ int rv_initial_conditions(rv_ctx* ctx, const rv_model* model, const double* thet
  * walker's grad / hess rows are zero.  Returns -30 when the model needs more than 448 (set, planet) threads.       */
 int rv_loglik_d_dd(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, const double* theta, int64_t W,
                    double* logp, double* grad, double* hess, int32_t* status);
+/* Same with the prior test chosen PER CALL (check_prior = 0: integrate even outside the hard prior, which is what
+ * State.get_logp_d_dd itself does, state.py:290-294) -- no model option is touched, so models shared between callers
+ * keep their behaviour.  The samplers (rv_smala_run, rv_alsmala_run) always test the prior (mcmc.py:171).          */
+int rv_loglik_d_dd_opt(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, const double* theta, int64_t W,
+                       int check_prior, double* logp, double* grad, double* hess, int32_t* status);
 /* Same with DEVICE buffers, asynchronous on `stream`. */
 int rv_loglik_d_dd_dev(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, const double* d_theta, int64_t W,
                        double* d_logp, double* d_grad, double* d_hess, int32_t* d_status, void* stream);

@@ -3,9 +3,12 @@
 This is the analogue of rebound's own ctypes layer (``clibrebound.reb_integrate(byref(sim), c_double(tmax))``
 reached from state.py:71): one thin call per *batch* of parameter vectors instead of one per epoch.
 """
+import collections
 import ctypes as C
+import hashlib
 import os
 import threading
+import weakref
 
 import numpy as np
 
@@ -48,6 +51,8 @@ _SIGNATURES = {
                                 C.c_void_p]),
     "rv_loglik_d_dd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_void_p]),
+    "rv_loglik_d_dd_opt": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_void_p]),
     "rv_loglik_d_dd_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_void_p]),
     "rv_initial_conditions": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
@@ -129,7 +134,13 @@ class Context(object):
             raise RvGpuError("rv_ctx_create failed (%d): %s" % (rc, self.lib.rv_last_error(None).decode()))
         self.h = h
         self.device = int(device)
-        self._models = {}
+        # Handle bookkeeping: every rv_obs / rv_model created on this context is tracked weakly and destroyed with it;
+        # the caches below only hold references (eviction drops a reference, it never frees a handle somebody else
+        # still uses -- the handle's own finalizer does that once it is unreferenced).
+        self._handles = weakref.WeakSet()
+        self._models = collections.OrderedDict()        # State schema key -> ModelHandle (LRU, see State._model)
+        self._obs = collections.OrderedDict()           # observation content digest -> ObsHandle (LRU, see obs_handle)
+        self._lock = threading.RLock()
 
     def check(self, rc, what):
         if rc != 0:
@@ -177,14 +188,68 @@ class Context(object):
         self.check(self.lib.rv_dev_copy_peer(dst_ctx.h, C.c_void_p(dst_addr), self.h, C.c_void_p(src_addr), int(nbytes)),
                    "rv_dev_copy_peer")
 
+    def cached(self, cache, key, make, limit=64):
+        """LRU lookup in one of this context's handle caches (thread-safe)."""
+        with self._lock:
+            h = cache.get(key)
+            if h is not None and getattr(h, "h", None):
+                cache.move_to_end(key)
+                return h
+            h = make()
+            cache[key] = h
+            while len(cache) > limit:
+                cache.popitem(last=False)              # drop OUR reference only
+            return h
+
+    def obs_handle(self, obs):
+        """rv_obs for an Observation-like object, keyed on the CONTENT of its arrays: editing or replacing
+        obs.rvf / errorf / tf ... (same length or not) re-uploads; the reference reads obs on every call."""
+        arrays = [_f64(getattr(obs, k)) for k in ("tf", "rvf", "errorf", "tb", "rvb", "errorb")]
+        dg = hashlib.blake2b(digest_size=16)
+        for a in arrays:
+            dg.update(np.int64(a.size).tobytes()); dg.update(a.tobytes())
+        dg.update(np.float64(obs.Npoints).tobytes())
+        return self.cached(self._obs, dg.digest(), lambda: ObsHandle(self, *arrays, obs.Npoints), limit=16)
+
     def close(self):
         if getattr(self, "h", None):
+            with self._lock:
+                for hd in list(self._handles):
+                    hd.close()
+                self._models.clear(); self._obs.clear()
             self.lib.rv_ctx_destroy(self.h)
             self.h = None
 
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
-class ObsHandle(object):
+
+class _Handle(object):
+    """Device object owned by a Context: destroyed explicitly, by its finalizer, or with the context."""
+    _destroy = None
+
+    def _register(self, ctx, h):
+        self.ctx, self.h = ctx, h
+        ctx._handles.add(self)
+
+    def close(self):
+        h, self.h = getattr(self, "h", None), None
+        if h and getattr(self.ctx, "h", None):          # a closed context has already released its device memory
+            getattr(self.ctx.lib, self._destroy)(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class ObsHandle(_Handle):
     """Observation arrays resident in HBM (rv_obs)."""
+    _destroy = "rv_obs_destroy"
 
     def __init__(self, ctx, tf, rvf, errf, tb, rvb, errb, npoints):
         self.ctx = ctx
@@ -195,16 +260,12 @@ class ObsHandle(object):
         h = C.c_void_p()
         ctx.check(ctx.lib.rv_obs_create(ctx.h, _ptr(tf), _ptr(rvf), _ptr(errf), len(tf), _ptr(tb), _ptr(rvb),
                                         _ptr(errb), len(tb), float(npoints), C.byref(h)), "rv_obs_create")
-        self.h = h
-
-    def close(self):
-        if getattr(self, "h", None):
-            self.ctx.lib.rv_obs_destroy(self.h)
-            self.h = None
+        self._register(ctx, h)
 
 
-class ModelHandle(object):
+class ModelHandle(_Handle):
     """Parameter schema resident in HBM (rv_model)."""
+    _destroy = "rv_model_destroy"
 
     def __init__(self, ctx, fixed, free_planet, free_elem, hill_factor, dims=0):
         self.ctx = ctx
@@ -216,7 +277,7 @@ class ModelHandle(object):
         h = C.c_void_p()
         ctx.check(ctx.lib.rv_model_create(ctx.h, self.n_planets, _ptr(fixed), self.nvars, _ptr(fp), _ptr(fe),
                                           float(hill_factor), int(dims), C.byref(h)), "rv_model_create")
-        self.h = h
+        self._register(ctx, h)
 
     def _theta(self, theta):
         theta = np.asarray(theta, dtype=np.float64)
@@ -255,11 +316,9 @@ class ModelHandle(object):
         grad = np.zeros((W, self.nvars), dtype=np.float64)
         hess = np.zeros((W, self.nvars, self.nvars), dtype=np.float64)
         status = np.empty(W, dtype=np.int32)
-        if bool(check_prior) != getattr(self, "_check_prior", True):
-            self.set_option("check_prior", 1.0 if check_prior else 0.0)
-            self._check_prior = bool(check_prior)
-        self.ctx.check(self.ctx.lib.rv_loglik_d_dd(self.ctx.h, self.h, obs.h, _ptr(theta), W, _ptr(logp), _ptr(grad),
-                                                   _ptr(hess), _ptr(status)), "rv_loglik_d_dd")
+        # the prior test is a per-call argument: the (possibly shared, cached) device model is never modified
+        self.ctx.check(self.ctx.lib.rv_loglik_d_dd_opt(self.ctx.h, self.h, obs.h, _ptr(theta), W, 1 if check_prior else 0,
+                                                       _ptr(logp), _ptr(grad), _ptr(hess), _ptr(status)), "rv_loglik_d_dd_opt")
         return logp, grad, hess, status
 
     def loglik_d_dd_dev(self, obs, d_theta, W, d_logp, d_grad, d_hess, d_status, stream=None):
@@ -390,21 +449,16 @@ class ModelHandle(object):
                                                     C.c_void_p(d_n_accept) if d_n_accept else None,
                                                     C.c_void_p(stream) if stream else None), "rv_mh_steps_dev")
 
-    def close(self):
-        if getattr(self, "h", None):
-            self.ctx.lib.rv_model_destroy(self.h)
-            self.h = None
-
-
 _default_ctx = None
 
 
 def default_context():
     """Process-wide context on cuda:LOCAL_RANK (or 0)."""
     global _default_ctx
-    if _default_ctx is None:
-        _default_ctx = Context(int(os.environ.get("LOCAL_RANK", "0")))
-    return _default_ctx
+    with _lib_lock:
+        if _default_ctx is None or not getattr(_default_ctx, "h", None):
+            _default_ctx = Context(int(os.environ.get("LOCAL_RANK", "0")))
+        return _default_ctx
 
 
 def set_default_context(ctx):

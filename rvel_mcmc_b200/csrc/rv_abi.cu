@@ -75,6 +75,15 @@ static int fail(rv_ctx* ctx, int code, const char* fmt, ...) {
         cudaError_t e__ = (call);                                                                  \
         if (e__ != cudaSuccess) return fail(ctx, -100, "%s: %s", #call, cudaGetErrorString(e__)); \
     } while (0)
+// same, running `cleanup` before the early return (create functions: nothing half-built may leak)
+#define CU_OR(ctx, call, cleanup)                                                                  \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            cleanup;                                                                               \
+            return fail(ctx, -100, "%s: %s", #call, cudaGetErrorString(e__));                      \
+        }                                                                                          \
+    } while (0)
 
 template <class T>
 static int ensure(rv_ctx* ctx, T** p, size_t* cap, size_t n) {
@@ -104,9 +113,14 @@ int rv_ctx_create(int device, rv_ctx** out) {
     if (!c) return fail(nullptr, -12, "rv_ctx_create: out of host memory");
     memset(c, 0, sizeof(*c));
     c->device = device;
-    CU(nullptr, cudaSetDevice(device));
+    auto drop = [&]() {
+        if (c->stream) cudaStreamDestroy(c->stream);
+        cudaFree(c->d_item_counter); cudaFree(c->d_work);
+        delete c;
+    };
+    CU_OR(nullptr, cudaSetDevice(device), drop());
     cudaDeviceProp prop;
-    CU(nullptr, cudaGetDeviceProperties(&prop, device));
+    CU_OR(nullptr, cudaGetDeviceProperties(&prop, device), drop());
     c->num_sms = prop.multiProcessorCount;
     c->cc_major = prop.major; c->cc_minor = prop.minor;
     int khz = 0;
@@ -116,11 +130,11 @@ int rv_ctx_create(int device, rv_ctx** out) {
         delete c;
         return fail(nullptr, -13, "rv_ctx_create: device %d is sm_%d%d; this library carries sm_100a code only", device, prop.major, prop.minor);
     }
-    CU(nullptr, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    CU(nullptr, cudaMalloc((void**)&c->d_item_counter, sizeof(unsigned long long)));
-    CU(nullptr, cudaMalloc((void**)&c->d_work, 2 * sizeof(unsigned long long)));
-    CU(nullptr, cudaMemset(c->d_item_counter, 0, sizeof(unsigned long long)));
-    CU(nullptr, cudaMemset(c->d_work, 0, 2 * sizeof(unsigned long long)));
+    CU_OR(nullptr, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), drop());
+    CU_OR(nullptr, cudaMalloc((void**)&c->d_item_counter, sizeof(unsigned long long)), drop());
+    CU_OR(nullptr, cudaMalloc((void**)&c->d_work, 2 * sizeof(unsigned long long)), drop());
+    CU_OR(nullptr, cudaMemset(c->d_item_counter, 0, sizeof(unsigned long long)), drop());
+    CU_OR(nullptr, cudaMemset(c->d_work, 0, 2 * sizeof(unsigned long long)), drop());
     *out = c;
     return 0;
 }
@@ -159,17 +173,18 @@ int rv_obs_create(rv_ctx* ctx, const double* tf, const double* rvf, const double
     CU(ctx, cudaSetDevice(ctx->device));
     rv_obs* o = new (std::nothrow) rv_obs();
     if (!o) return fail(ctx, -12, "out of host memory");
-    o->ctx = ctx; o->nf = nf; o->nb = nb; o->npoints = npoints;
+    o->ctx = ctx; o->nf = nf; o->nb = nb; o->npoints = npoints; o->d_t = nullptr;
     const size_t n = (size_t)nf + nb;
-    CU(ctx, cudaMalloc((void**)&o->d_t, 3 * n * sizeof(double)));
+    auto drop = [&]() { cudaFree(o->d_t); delete o; };
+    CU_OR(ctx, cudaMalloc((void**)&o->d_t, 3 * n * sizeof(double)), drop());
     o->d_rv = o->d_t + n; o->d_err = o->d_t + 2 * n;
     const double* srcs[3][2] = {{tf, tb}, {rvf, rvb}, {errf, errb}};
     double* dsts[3] = {o->d_t, o->d_rv, o->d_err};
     for (int a = 0; a < 3; a++) {
-        if (nf) CU(ctx, cudaMemcpyAsync(dsts[a], srcs[a][0], nf * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-        if (nb) CU(ctx, cudaMemcpyAsync(dsts[a] + nf, srcs[a][1], nb * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        if (nf) CU_OR(ctx, cudaMemcpyAsync(dsts[a], srcs[a][0], nf * sizeof(double), cudaMemcpyHostToDevice, ctx->stream), drop());
+        if (nb) CU_OR(ctx, cudaMemcpyAsync(dsts[a] + nf, srcs[a][1], nb * sizeof(double), cudaMemcpyHostToDevice, ctx->stream), drop());
     }
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU_OR(ctx, cudaStreamSynchronize(ctx->stream), drop());
     *out = o;
     return 0;
 }
@@ -193,9 +208,10 @@ int rv_model_create(rv_ctx* ctx, int n_planets, const double* fixed, int nvars, 
         delete m;
         return fail(ctx, rc, "rv_model_create: invalid model (code %d): planets must be 1..%d, slots unique and in range, dims 0/2/3", rc, rv::MAXP);
     }
-    CU(ctx, cudaSetDevice(ctx->device));
-    CU(ctx, cudaMalloc((void**)&m->d, sizeof(rv::Model)));
-    CU(ctx, cudaMemcpy(m->d, &m->h, sizeof(rv::Model), cudaMemcpyHostToDevice));
+    auto drop = [&]() { cudaFree(m->d); delete m; };
+    CU_OR(ctx, cudaSetDevice(ctx->device), drop());
+    CU_OR(ctx, cudaMalloc((void**)&m->d, sizeof(rv::Model)), drop());
+    CU_OR(ctx, cudaMemcpy(m->d, &m->h, sizeof(rv::Model), cudaMemcpyHostToDevice), drop());
     *out = m;
     return 0;
 }
@@ -356,8 +372,10 @@ int rv_initial_conditions(rv_ctx* ctx, const rv_model* model, const double* thet
 // ------------------------------------------------------------------------------------------------
 // value + gradient + Hessian
 
+// check_prior is a per-call argument: the samplers always test priorHard (mcmc.py:171), whatever the model option says;
+// the plain entry points follow the model option (default 1), rv_loglik_d_dd_opt takes it from the caller.
 static int var_dev_impl(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, const double* d_theta, int64_t W,
-                        double* d_logp, double* d_grad, double* d_hess, int32_t* d_status, cudaStream_t s) {
+                        double* d_logp, double* d_grad, double* d_hess, int32_t* d_status, int check_prior, cudaStream_t s) {
     if (W == 0) return 0;
     const int nv = model->h.nvars;
     if (model->h.integrator != 0)
@@ -373,6 +391,7 @@ static int var_dev_impl(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, c
     a.model = model->d; a.theta = d_theta; a.W = W;
     a.ot = obs->d_t; a.orv = obs->d_rv; a.oerr = obs->d_err; a.nf = obs->nf; a.nb = obs->nb;
     a.npoints = obs->npoints;
+    a.check_prior = check_prior ? 1 : 0;
     a.part = ctx->d_vpart; a.part_status = ctx->d_pstat;
     a.item_counter = ctx->d_item_counter;
     a.work_counters = ctx->count_work ? ctx->d_work : nullptr;
@@ -386,11 +405,17 @@ int rv_loglik_d_dd_dev(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, co
     if (!ctx || !model || !obs) return fail(ctx, -1, "rv_loglik_d_dd_dev: NULL handle");
     if (W < 0) return fail(ctx, -2, "rv_loglik_d_dd_dev: negative W");
     CU(ctx, cudaSetDevice(ctx->device));
-    return var_dev_impl(ctx, model, obs, d_theta, W, d_logp, d_grad, d_hess, d_status, (cudaStream_t)stream);
+    return var_dev_impl(ctx, model, obs, d_theta, W, d_logp, d_grad, d_hess, d_status, model->h.check_prior, (cudaStream_t)stream);
 }
 
 int rv_loglik_d_dd(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, const double* theta, int64_t W,
                    double* logp, double* grad, double* hess, int32_t* status) {
+    if (!model) return fail(ctx, -1, "rv_loglik_d_dd: NULL handle");
+    return rv_loglik_d_dd_opt(ctx, model, obs, theta, W, model->h.check_prior, logp, grad, hess, status);
+}
+
+int rv_loglik_d_dd_opt(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, const double* theta, int64_t W,
+                       int check_prior, double* logp, double* grad, double* hess, int32_t* status) {
     if (!ctx || !model || !obs) return fail(ctx, -1, "rv_loglik_d_dd: NULL handle");
     if (W < 0) return fail(ctx, -2, "rv_loglik_d_dd: negative W");
     if (W == 0) return 0;
@@ -405,7 +430,7 @@ int rv_loglik_d_dd(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, const 
     if (int rc = ensure(ctx, &ctx->d_hess, &ctx->cap_hess, (size_t)W * nvs * nvs)) return rc;
     cudaStream_t s = ctx->stream;
     if (nv > 0) CU(ctx, cudaMemcpyAsync(ctx->d_theta, theta, (size_t)W * nv * sizeof(double), cudaMemcpyHostToDevice, s));
-    if (int rc = var_dev_impl(ctx, model, obs, ctx->d_theta, W, ctx->d_logp, ctx->d_grad, ctx->d_hess, ctx->d_status, s)) return rc;
+    if (int rc = var_dev_impl(ctx, model, obs, ctx->d_theta, W, ctx->d_logp, ctx->d_grad, ctx->d_hess, ctx->d_status, check_prior, s)) return rc;
     CU(ctx, cudaMemcpyAsync(logp, ctx->d_logp, (size_t)W * sizeof(double), cudaMemcpyDeviceToHost, s));
     CU(ctx, cudaMemcpyAsync(status, ctx->d_status, (size_t)W * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     if (nv > 0) {
@@ -620,7 +645,7 @@ static int smala_impl(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, dou
     CU(ctx, cudaMemcpyAsync(ctx->d_theta, theta, (size_t)W * nv * sizeof(double), cudaMemcpyHostToDevice, s));
     CU(ctx, cudaMemsetAsync(ctx->d_nacc, 0, (size_t)W * sizeof(unsigned long long), s));
     // state.get_logp_d_dd at the start state (mcmc.py:145)
-    if (int rc = var_dev_impl(ctx, model, obs, ctx->d_theta, W, ctx->d_logp, ctx->d_grad, ctx->d_hess, ctx->d_status, s)) return rc;
+    if (int rc = var_dev_impl(ctx, model, obs, ctx->d_theta, W, ctx->d_logp, ctx->d_grad, ctx->d_hess, ctx->d_status, 1, s)) return rc;
     CU(ctx, cudaMemcpyAsync(ctx->d_flag, ctx->d_status, (size_t)W * sizeof(int), cudaMemcpyDeviceToDevice, s));
     long long row = 0;
     for (int k = 0; k < nsteps; k++) {
@@ -637,7 +662,7 @@ static int smala_impl(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, dou
         if (mala) {
             if (int rc = loglik_dev_impl(ctx, model, obs, ctx->d_prop, W, ctx->d_plogp, ctx->d_pstatus, s)) return rc;
         } else {
-            if (int rc = var_dev_impl(ctx, model, obs, ctx->d_prop, W, ctx->d_plogp, ctx->d_pgrad, ctx->d_phess, ctx->d_pstatus, s)) return rc;
+            if (int rc = var_dev_impl(ctx, model, obs, ctx->d_prop, W, ctx->d_plogp, ctx->d_pgrad, ctx->d_phess, ctx->d_pstatus, 1, s)) return rc;
         }
         const bool rec = rows && ((k + 1) % thin == 0);
         CU(ctx, rv::launch_smala_accept(ctx->d_theta, ctx->d_logp, ctx->d_grad, ctx->d_hess, ctx->d_prop, ctx->d_plogp,
@@ -736,25 +761,25 @@ int rv_fp64_peak(rv_ctx* ctx, double* tflops) {
     if (!ctx || !tflops) return -1;
     CU(ctx, cudaSetDevice(ctx->device));
     double* d = nullptr;
-    CU(ctx, cudaMalloc((void**)&d, 64));
-    cudaEvent_t e0, e1;
-    CU(ctx, cudaEventCreate(&e0));
-    CU(ctx, cudaEventCreate(&e1));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    auto drop = [&]() { if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); cudaFree(d); };
+    CU_OR(ctx, cudaMalloc((void**)&d, 64), drop());
+    CU_OR(ctx, cudaEventCreate(&e0), drop());
+    CU_OR(ctx, cudaEventCreate(&e1), drop());
     const int blocks = ctx->num_sms * 8, iters = 4096;
     double best = 0.0;
     for (int rep = 0; rep < 6; rep++) {
-        CU(ctx, cudaEventRecord(e0, ctx->stream));
-        CU(ctx, rv::launch_fp64_peak(d, blocks, iters, ctx->stream));
-        CU(ctx, cudaEventRecord(e1, ctx->stream));
-        CU(ctx, cudaEventSynchronize(e1));
+        CU_OR(ctx, cudaEventRecord(e0, ctx->stream), drop());
+        CU_OR(ctx, rv::launch_fp64_peak(d, blocks, iters, ctx->stream), drop());
+        CU_OR(ctx, cudaEventRecord(e1, ctx->stream), drop());
+        CU_OR(ctx, cudaEventSynchronize(e1), drop());
         float ms = 0;
-        CU(ctx, cudaEventElapsedTime(&ms, e0, e1));
+        CU_OR(ctx, cudaEventElapsedTime(&ms, e0, e1), drop());
         const double flops = 2.0 * 64.0 * (double)iters * 256.0 * (double)blocks;
         const double tf = flops / (ms * 1e-3) / 1e12;
         if (rep > 0 && tf > best) best = tf;
     }
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
-    cudaFree(d);
+    drop();
     *tflops = best;
     return 0;
 }

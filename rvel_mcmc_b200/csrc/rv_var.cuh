@@ -22,6 +22,8 @@ struct VarArgs {
     const double *ot, *orv, *oerr;   // forward leg [0,nf), backward leg [nf,nf+nb) in obs.tb (ascending) order
     int nf, nb;
     double npoints;        // the `fac` of state.py:258
+    int check_prior;       // per call: 1 = test priorHard first (status ST_PRIOR, no integration), 0 = integrate regardless
+                           // (State.get_logp_d_dd itself has no prior test, state.py:290-294; the samplers do, mcmc.py:171)
     double* part;          // [2W][nsets]: chi2, d[a], dd[a][b] (a >= b, row-major in a) of one leg
     int* part_status;      // [2W]: item w = backward leg of walker w, item W+w = forward leg
     unsigned long long* item_counter;
@@ -489,7 +491,7 @@ RV_D void var_run_items(Exec& ex, const VarArgs& a, const VarLayout& L, double* 
         }
         int final_status = -1;
         unsigned long long n_force = 0, n_attempt = 0;
-        if (bad && md->check_prior) final_status = ST_PRIOR;
+        if (bad && a.check_prior) final_status = ST_PRIOR;
         if (final_status < 0) {
 #pragma unroll
             for (int i = 0; i < P; i++) {

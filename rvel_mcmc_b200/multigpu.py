@@ -78,17 +78,23 @@ class DeviceGroup(object):
                 out[k] = np.concatenate(vals, axis=0)
         return out
 
-    def mh_run(self, state, obs, theta, scales, step_size, nsteps, seed=0, **kw):
+    def mh_run(self, state, obs, theta, scales, step_size, nsteps, seed=0, logp=None, first_chain_id=0, **kw):
         theta = np.ascontiguousarray(theta, dtype=np.float64)
         hs = self._handles(state, obs)
+        if logp is not None:
+            logp = np.ascontiguousarray(logp, dtype=np.float64)
+            if logp.shape != (len(theta),):
+                raise ValueError("logp must hold one value per chain")
+        # per-chain arguments are sliced with the chains; the RNG streams are keyed by the GLOBAL chain id
         return self._merge(self._map(len(theta), lambda r, lo, hi: hs[r][0].mh_run(
-            hs[r][1], theta[lo:hi], scales, step_size, nsteps, seed=seed, first_chain_id=lo, **kw)))
+            hs[r][1], theta[lo:hi], scales, step_size, nsteps, seed=seed, first_chain_id=first_chain_id + lo,
+            logp=None if logp is None else logp[lo:hi], **kw)))
 
-    def smala_run(self, state, obs, theta, eps, alpha, nsteps, seed=0, **kw):
+    def smala_run(self, state, obs, theta, eps, alpha, nsteps, seed=0, first_chain_id=0, **kw):
         theta = np.ascontiguousarray(theta, dtype=np.float64)
         hs = self._handles(state, obs)
         return self._merge(self._map(len(theta), lambda r, lo, hi: hs[r][0].smala_run(
-            hs[r][1], theta[lo:hi], eps, alpha, nsteps, seed=seed, first_chain_id=lo, **kw)))
+            hs[r][1], theta[lo:hi], eps, alpha, nsteps, seed=seed, first_chain_id=first_chain_id + lo, **kw)))
 
 
 def _stretch_run(group, state, obs, theta0, nsteps, a=2.0, seed=0):
@@ -159,10 +165,5 @@ DeviceGroup.stretch_run = lambda self, state, obs, theta0, nsteps, a=2.0, seed=0
 
 
 def _obs_handle(obs, ctx):
-    """One rv_obs per context (Observation._handle keeps a single-entry cache, so groups keep their own)."""
-    cache = obs.__dict__.setdefault("_rv_group_handles", {})
-    h = cache.get(id(ctx))
-    if h is None:
-        h = _abi.ObsHandle(ctx, obs.tf, obs.rvf, obs.errorf, obs.tb, obs.rvb, obs.errorb, obs.Npoints)
-        cache[id(ctx)] = h
-    return h
+    """One rv_obs per context, from that context's content-keyed cache (closed with the context)."""
+    return ctx.obs_handle(obs)

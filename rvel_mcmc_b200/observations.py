@@ -21,16 +21,11 @@ class Observation(object):
     rv = None
     err = None
 
-    # --- GPU residency (not in the reference): one rv_obs per (context) ---
+    # --- GPU residency (not in the reference): the device copy lives in the Context's cache, keyed on the CONTENT of the
+    # arrays, so edited / replaced data is re-uploaded (the reference reads obs on every call) and nothing outlives
+    # its context ---
     def _handle(self, ctx):
-        cache = self.__dict__.setdefault("_rv_handles", {})
-        key = (id(ctx), float(self.Npoints), len(self.tf), len(self.tb))
-        h = cache.get(key)
-        if h is None:
-            h = _abi.ObsHandle(ctx, self.tf, self.rvf, self.errorf, self.tb, self.rvb, self.errorb, self.Npoints)
-            cache.clear()
-            cache[key] = h
-        return h
+        return ctx.obs_handle(self)
 
 
 def _join_legs(obs):

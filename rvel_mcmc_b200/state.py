@@ -117,12 +117,7 @@ class State(object):
             fixed_key[p, e] = 0.0
         whfast = {"ias15": 0, "whfast": 1}[self.integrator]
         key = (tuple(fp), tuple(fe), fixed_key.tobytes(), float(hf), whfast, float(self.dt), bool(self.dense_output))
-        m = ctx._models.get(key)
-        if m is None:
-            if len(ctx._models) > 64:
-                for old in ctx._models.values():
-                    old.close()
-                ctx._models.clear()
+        def make():
             m = _abi.ModelHandle(ctx, fixed, fp, fe, hf)
             if whfast or self.dt != 0.001:
                 m.set_option("dt0", self.dt)
@@ -130,8 +125,10 @@ class State(object):
                 m.set_option("integrator", 1)
             if self.dense_output:
                 m.set_option("dense_output", 1)
-            ctx._models[key] = m
-        return m
+            return m
+        # LRU cache on the context: eviction only drops the cache's reference; a handle still held by a caller (a
+        # DeviceGroup, another thread) stays valid and is freed by its own finalizer
+        return ctx.cached(ctx._models, key, make, limit=64)
 
     # ------------------------------------------------------------------ reference API
     def setup_sim(self):

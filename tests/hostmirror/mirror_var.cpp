@@ -53,7 +53,7 @@ extern "C" int mirror_loglik_d_dd(int P, const double* fixed, int nvars, const i
     rv::VarArgs a;
     memset(&a, 0, sizeof a);
     a.model = &m; a.theta = theta; a.W = W;
-    a.ot = ot.data(); a.orv = orv.data(); a.oerr = oerr.data(); a.nf = nf; a.nb = nb; a.npoints = npoints;
+    a.ot = ot.data(); a.orv = orv.data(); a.oerr = oerr.data(); a.nf = nf; a.nb = nb; a.npoints = npoints; a.check_prior = m.check_prior;
     a.part = part.data(); a.part_status = pst.data(); a.item_counter = &ctr; a.work_counters = work;
     const int key = P * 10 + m.D;
     switch (key) {

@@ -160,3 +160,54 @@ def test_non_finite_parameters_are_reported_not_hung(ctx):
     m.set_option("integrator", 1); m.set_option("dt0", 0.1)
     lg, sg = m.loglik(oh, theta)
     assert sg[5] == 0 and (sg[:5] != 0).all()
+
+
+def test_prior_test_is_per_call_not_sticky_on_shared_models():
+    """State.get_logp_d_dd integrates outside the hard prior (state.py:290-294); that must not switch the prior test off
+    for later callers of the same cached device model (the samplers always reject priorHard violations, mcmc.py:171)."""
+    import os
+    from rvel_mcmc_b200 import observations, state, _abi
+    obs = observations.Observation_FromFile(os.path.join(T.GOLDEN, "HD155358.vels"), Npoints=100)
+    st = state.State(T.planets_from_vec(T.HD_SOL)); st.hillRadiusFactor = 2.
+    ctx = _abi.default_context()
+    m, oh = st._model(ctx), obs._handle(ctx)
+    bad = np.array(T.HD_SOL); bad[3] = 4e-6                        # m <= 5e-6
+    out = state.State(T.planets_from_vec(bad)); out.hillRadiusFactor = 2.
+    assert out._model(ctx) is m                                    # same schema -> same cached device model
+    lp, d, dd = out.get_logp_d_dd(obs)                             # no prior test on this path
+    assert np.isfinite(lp) and np.isfinite(d).all()
+    theta = np.array([T.HD_SOL, bad])
+    lg, gg, hg, sg = m.loglik_d_dd(oh, theta)
+    assert list(sg) == [0, 1] and np.isneginf(lg[1]) and (gg[1] == 0).all()
+    r = m.smala_run(oh, theta, 0.025, 1.4, 3, seed=1)
+    assert r["status"][1] == 1 and r["n_accept"][1] == 0           # a chain started outside the prior never moves
+    assert np.array_equal(r["theta"][1], bad)
+    lg2, _, _, sg2 = m.loglik_d_dd(oh, theta, check_prior=False)
+    assert list(sg2) == [0, 0] and abs(lg2[1] - lp) < 1e-12
+
+
+def test_observation_edits_reach_the_device():
+    """The reference reads obs on every call; the device copy is keyed on content, so edits are never served stale."""
+    import os
+    from rvel_mcmc_b200 import observations, state, _abi
+    obs = observations.Observation_FromFile(os.path.join(T.GOLDEN, "HD155358.vels"), Npoints=100)
+    st = state.State(T.planets_from_vec(T.HD_SOL)); st.hillRadiusFactor = 2.
+    l0 = st.get_logp(obs)
+    assert abs(l0 - T.KAT2_LOGP) < 5e-11
+    h0 = obs._handle(_abi.default_context())
+    assert obs._handle(_abi.default_context()) is h0               # unchanged data: same device copy
+    obs.rvf[3] += 5e-4                                             # in-place edit, same length
+    st.logp = None
+    l1 = st.get_logp(obs)
+    assert abs(l1 - l0) > 1e-6
+    obs.rvf = obs.rvf.copy(); obs.rvf[3] -= 5e-4                   # replaced array
+    st.logp = None
+    assert abs(st.get_logp(obs) - l0) < 1e-12
+    obs.Npoints = 50
+    st.logp = None
+    assert abs(st.get_logp(obs) - 2 * l0) < 1e-9
+    # handles do not outlive their context
+    c2 = _abi.Context(0)
+    h2 = obs._handle(c2)
+    c2.close()
+    assert h2.h is None
