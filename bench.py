@@ -1,18 +1,28 @@
 #!/usr/bin/env python3
-"""bench.py -- headline benchmark of the hot path (BASELINE.json: RV log-lik evals/sec, HD155358 2-planet).
+"""bench.py -- headline benchmark of the hot path (BASELINE.json: RV log-lik evals/sec & ESS/sec, HD155358 2-planet).
 
 One "step" = one pass of the hot path over one batch of synthetic walkers: the log-likelihood
 (State.get_logp, state.py:103) of `--walkers` parameter vectors per GPU drawn as the reference's ensemble
 start ball (mcmc.py:49-51) around the published HD155358 solution, on the real HD155358.vels epochs
 (122 epochs, Npoints=100, hillRadiusFactor=2).  Weak scaling: every rank owns its own walker shard, no
-data-path collective.
+data-path collective in the headline loop.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--walkers 65536] [--impl reference]
+                  [--no-ess] [--no-var] [--no-sharded] [--ess-rows 2000] [--quick]
 
 Prints ONE JSON line (rank 0).  `value` = evaluations/s with inputs resident in HBM (CUDA events on the
 launching stream, max over ranks); `e2e` = the same through the host-buffer C-ABI call rv_loglik (pinned
-host memory, H2D + D2H inside the timed region).  `--impl reference` times the reference's CPU path:
-the oracle port of rebound's algorithm (oracle/, OpenMP over all host cores) on a bounded sample.
+host memory, H2D + D2H inside the timed region).  Beside the headline the line carries
+  * `ess`             ESS/s of the stretch / MH / SMALA device samplers from a committed EQUILIBRATED ensemble
+                      (tests/golden/hd155358_equilibrated_ensemble.npy), >= 2000 recorded rows, reference AC time
+                      (driver.py:366-377) and Sokal's integrated time; at N > 1 every rank runs its own chains /
+                      ensemble replica and the aggregate is sum(ESS) / max(seconds);
+  * `var`             value + gradient + Hessian evaluations/s (State.get_logp_d_dd) and that kernel's roofline;
+  * `stretch_sharded` (N > 1) the affine ensemble sharded over the ranks with the per-half-step NCCL all-gather:
+                      weak (56 832 walkers per GPU) and strong (65 536 walkers in total) evals/s, CUDA-event split
+                      kernel / all-gather, host share, bit-identity against the single-GPU ensemble.
+`--impl reference` times the reference's CPU path: the oracle port of rebound's algorithm (oracle/, OpenMP over
+all host cores) on a bounded sample.
 """
 import argparse
 import json
@@ -35,6 +45,8 @@ HD_SOL = [6.57730330e-01, -9.72263877e-02, -7.82798396e-02, 8.84031737e-04, 4.42
 HD_SCALES = {"m": 5.5e-6, "a": 0.001, "h": 0.02, "k": 0.02, "l": np.pi / 4}
 FP10 = [0, 0, 0, 0, 0, 1, 1, 1, 1, 1]
 FE10 = [1, 2, 3, 0, 4, 1, 2, 3, 0, 4]
+EQUILIBRATED = os.path.join(ROOT, "tests", "golden", "hd155358_equilibrated_ensemble.npy")
+ROOFLINE_INPUTS = os.path.join(ROOT, "profiles", "roofline_inputs.json")     # ncu-derived figures, one file, committed
 
 
 def walker_ball(W, seed):
@@ -51,6 +63,24 @@ def load_obs():
 def flops_per_eval(S, T):
     """W_eval = S*[3N*36 + N(N-1)*18] + T*3N*150 with N = 3 bodies."""
     return S * (9 * 36 + 6 * 18) + T * 9 * 150
+
+
+def var_flops_per_eval(S, T, nv=10, N=3):
+    """SURVEY 8(d), variational evaluation: per force evaluation 3*(30 + nv*45 + nv(nv+1)/2*140) gravity flops plus 36 per
+    coordinate of the (1 + nv + nv(nv+1)/2) sets of N bodies; per step attempt 150 per coordinate."""
+    n2 = nv * (nv + 1) // 2
+    coords = 3 * N * (1 + nv + n2)
+    return S * (3 * (30 + nv * 45 + n2 * 140) + coords * 36) + T * coords * 150
+
+
+def roofline_inputs():
+    """Figures that only a profiler can give (DRAM traffic per launch, FP64-pipe utilisation): read from ONE committed
+    file that names the ncu summary each comes from -- never typed into this script."""
+    try:
+        with open(ROOFLINE_INPUTS) as f:
+            return json.load(f)
+    except Exception:
+        return {}
 
 
 class ClockSampler(threading.Thread):
@@ -94,38 +124,174 @@ def oracle_batch(obs, theta, nthreads):
     return time.perf_counter() - t0, logp, st, cnt
 
 
-def run_ess(ctx, model, oh):
-    """ESS/s of the three device samplers on the HD155358 posterior (bounded runs; reference AC definition + Sokal tau)."""
+# ---------------------------------------------------------------------------------------------------------------
+# ESS/s (BASELINE metric, second half): the three device samplers from an equilibrated start
+
+def run_ess(ctx, model, oh, rank, world, dist, dev, rows, torch):
     from rvel_mcmc_b200.samplers import ess
     from rvel_mcmc_b200 import driver
-    out = {}
-    sc = np.array([HD_SCALES[k] for k in ("a", "h", "k", "m", "l")] * 2)
+    if not os.path.exists(EQUILIBRATED):
+        return {"unavailable": "tests/golden/hd155358_equilibrated_ensemble.npy is missing (tools/make_equilibrated_ensemble.py)"}
+    eq = np.load(EQUILIBRATED)
+    post_std = eq.std(axis=0)
+    slots = ctx.device_info()["sm_count"] * 3 * 64          # resident (walker, leg) lane groups of loglik_kernel
+    out = {"start": "committed equilibrated stretch ensemble (%d walkers; tools/make_equilibrated_ensemble.py), no burn-in "
+                    "inside the clock" % len(eq),
+           "definition": "ESS = recorded rows x walkers / max_i tau_i; tau_int = Sokal's windowed integrated autocorrelation "
+                         "time (mean over 64 walkers per parameter), ac_time_ref = driver.py:366-377 (first lag with "
+                         "autocorrelation < 0.5; mean over 16 walkers, as driver.py:355-370 does for ensembles); seconds = "
+                         "wall time of the whole library call (chain download included)",
+           "aggregate": "sum over ranks of ESS / max over ranks of seconds; every rank runs its own chains (MH, SMALA: "
+                        "global chain ids) or its own ensemble replica (stretch: rank-specific seed)"}
 
-    def summarise(name, chain, seconds, evals, burn):
-        c = chain[burn:]
-        n_eff, tau = ess(c)
-        ac_ref = max(driver.ac_time(c[:, 0, i]) for i in range(c.shape[2]))     # driver.py:366-377 (first lag with AC < 0.5)
-        # ESS of the post-burn-in samples divided by the WHOLE run time (burn-in included); tau in recorded rows
-        out[name] = {"walkers": int(chain.shape[1]), "recorded_rows": int(chain.shape[0]), "seconds": seconds,
-                     "evals_per_s": evals / seconds, "tau_int_max_rows": tau, "ac_time_ref_max_rows": ac_ref,
-                     "ess_per_s": n_eff / seconds}
+    def summarise(name, chain, seconds, evals, extra):
+        n_eff, tau = ess(chain)
+        ac_ref = max(float(np.mean([driver.ac_time(chain[:, w, i]) for w in range(min(16, chain.shape[1]))]))
+                     for i in range(chain.shape[2]))
+        vals = [float(n_eff), float(seconds), float(evals)]
+        if world > 1:
+            t = torch.tensor(vals, dtype=torch.float64, device=dev)
+            s = t.clone(); dist.all_reduce(s, op=dist.ReduceOp.SUM)
+            m = t.clone(); dist.all_reduce(m, op=dist.ReduceOp.MAX)
+            n_eff_tot, sec, ev = float(s[0]), float(m[1]), float(s[2])
+        else:
+            n_eff_tot, sec, ev = vals
+        d = {"walkers_per_gpu": int(chain.shape[1]), "recorded_rows": int(chain.shape[0]), "seconds": sec,
+             "evals_per_s": ev / sec, "tau_int_max_rows": tau, "ac_time_ref_max_rows": ac_ref,
+             "ess_per_s": n_eff_tot / sec, "ess_per_s_ref_definition": n_eff_tot * max(tau, 1.0) / max(ac_ref, 1.0) / sec}
+        d.update(extra)
+        out[name] = d
 
-    # walker counts that fill the machine: 3 CTAs x 64 lane groups per SM, one (walker, leg) item per group
+    # affine stretch: one full wave of (walker, leg) items per half-step
+    W = min(len(eq), slots) & ~1
+    t0 = time.perf_counter()
+    r = model.stretch_run(oh, eq[:W], rows, seed=11 + 1000 * rank, thin=1)
+    summarise("stretch", r["chain"], time.perf_counter() - t0, W * (rows + 1),
+              {"accept_rate": float(r["n_accept"].mean() / rows), "a": 2.0})
+    del r
+    # Metropolis-Hastings: proposal scale 0.25 x the posterior standard deviations of the equilibrated ensemble
+    W = min(len(eq), slots // 2)
+    t0 = time.perf_counter()
+    r = model.mh_run(oh, eq[:W], post_std, 0.25, rows, seed=12, first_chain_id=rank * W, thin=1)
+    summarise("mh", r["chain"], time.perf_counter() - t0, W * (rows + 1),
+              {"accept_rate": float(r["n_accept"].mean() / rows), "step_size": 0.25, "scales": "posterior std"})
+    del r
+    # SMALA with the reference's step size and SoftAbs constant ((Ex)HD155358.ipynb:640): one wave of var_kernel CTAs
+    W = ctx.device_info()["sm_count"] * 3 // 2
+    t0 = time.perf_counter()
+    r = model.smala_run(oh, eq[:W], 0.025, 1.4, rows, seed=13, first_chain_id=rank * W, thin=1)
+    summarise("smala", r["chain"], time.perf_counter() - t0, W * (rows + 1),
+              {"accept_rate": float(r["n_accept"].mean() / rows), "eps": 0.025, "alpha": 1.4,
+               "not_spd_flags": int((r["status"] == 9).sum())})
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# value + gradient + Hessian (State.get_logp_d_dd): var_kernel throughput and roofline
+
+def run_var(ctx, model, oh, dev, peak, torch):
+    W = ctx.device_info()["sm_count"] * 3 // 2 * 8          # eight waves of CTAs
+    th = torch.from_numpy(walker_ball(W, 4242)).to(dev)
+    lp = torch.empty(W, dtype=torch.float64, device=dev); st = torch.empty(W, dtype=torch.int32, device=dev)
+    g = torch.empty((W, 10), dtype=torch.float64, device=dev); h = torch.empty((W, 10, 10), dtype=torch.float64, device=dev)
+    s = torch.cuda.current_stream().cuda_stream
+
+    def call():
+        model.loglik_d_dd_dev(oh, th.data_ptr(), W, lp.data_ptr(), g.data_ptr(), h.data_ptr(), st.data_ptr(), s)
+    call(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); call(); e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    ctx.count_work(True); ctx.work_counters(reset=True)
+    call(); torch.cuda.synchronize()
+    S, T_ = ctx.work_counters(reset=True)
+    ctx.count_work(False)
+    S, T_ = S / W, T_ / W
+    fl = var_flops_per_eval(S, T_)
+    achieved = fl * W / (ms * 1e-3) / 1e12
+    prof = roofline_inputs().get("var_kernel", {})
+    return {"value": W / (ms * 1e-3), "unit": "value+gradient+Hessian evals/s per GPU", "walkers": W, "ms": ms,
+            "ok_fraction": float((st == 0).float().mean().item()),
+            "roofline": {"bound": "fp64_fma_pipe", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                         "note": "SURVEY 8(d) algorithmic flops of the variational evaluation (S=%.0f force evaluations, T=%.0f "
+                                 "step attempts per eval, real-only step-size norm) / CUDA-event time" % (S, T_),
+                         "from_profile": prof},
+            "reference": "0.58 tries/s (rebound + Python 2, one 2017 core; (Ex)HD155358.ipynb:628-640) -- context only"}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# N > 1: the affine ensemble sharded over the ranks, all-gather of the updated half after every half-step
+
+def run_stretch_sharded(ctx, model, oh, rank, world, dist, dev, torch, nsteps):
+    from rvel_mcmc_b200.samplers import ShardedStretch
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    out = {"exchange": "torch.distributed all_gather_into_tensor (NCCL) of the updated half-ensemble's positions after every "
+                       "half-step; random numbers keyed by ensemble index, nothing else crosses ranks"}
     slots = ctx.device_info()["sm_count"] * 3 * 64
-    W, n = 2 * slots, 300                   # each half-ensemble = one backward + one forward round
-    t0 = time.perf_counter()
-    r = model.stretch_run(oh, walker_ball(W, 5), n, seed=11, thin=2)
-    summarise("stretch", r["chain"], time.perf_counter() - t0, W * (n + 1), n // 8)
-    out["stretch"]["thin"] = 2
-    W, n = slots, 300
-    t0 = time.perf_counter()
-    r = model.mh_run(oh, walker_ball(W, 6), sc, 0.1, n, seed=12, thin=2)
-    summarise("mh", r["chain"], time.perf_counter() - t0, W * (n + 1), n // 8)
-    out["mh"]["thin"] = 2
-    W, n = 2368, 60
-    t0 = time.perf_counter()
-    r = model.smala_run(oh, walker_ball(W, 7), 0.025, 1.4, n, seed=13, thin=1)
-    summarise("smala", r["chain"], time.perf_counter() - t0, W * (n + 1), n // 4)
+
+    def one(W, label):
+        theta0 = walker_ball(W, 5)
+        theta = torch.from_numpy(theta0).to(dev)
+        h, n_loc = W // 2, (W // 2) // world
+        lnp = torch.empty(2 * n_loc, dtype=torch.float64, device=dev)
+        stl = torch.empty(2 * n_loc, dtype=torch.int32, device=dev)
+        for half in (0, 1):
+            lo = half * h + rank * n_loc
+            model.loglik_dev(oh, theta[lo:lo + n_loc].data_ptr(), n_loc, lnp[half * n_loc:].data_ptr(), stl[half * n_loc:].data_ptr(), stream)
+        lnp[stl != 0] = float("-inf")
+        send = torch.empty((n_loc, 10), dtype=torch.float64, device=dev)
+
+        def half_step(k, half, ev=None):
+            lo = half * h + rank * n_loc
+            S = theta[lo:lo + n_loc]
+            C = theta[h:] if half == 0 else theta[:h]
+            if ev: ev[0].record()
+            model.stretch_half_dev(oh, S.data_ptr(), n_loc, lo, C.data_ptr(), h, lnp[half * n_loc:].data_ptr(), 2.0, 5, k, half,
+                                   stream=stream)
+            if ev: ev[1].record()
+            send.copy_(S)
+            dist.all_gather_into_tensor(theta[half * h:(half + 1) * h], send)
+            if ev: ev[2].record()
+        half_step(0, 0); half_step(0, 1)                       # warm-up (NCCL channels, scratch growth)
+        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(2 * nsteps)]
+        t0 = time.perf_counter()
+        for k in range(nsteps):
+            for half in (0, 1):
+                half_step(1 + k, half, evs[2 * k + half])
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        kern = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
+        gath = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
+        t = torch.tensor([wall, kern, gath], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        wall, kern, gath = [float(x) for x in t]
+        per_half = 1e3 * wall / (2 * nsteps)
+        d = {"walkers_total": W, "walkers_per_gpu": W // world, "ensemble_steps": nsteps,
+             "evals_per_s": W * nsteps / wall, "ms_per_half_step": per_half, "kernel_ms_per_half_step": kern,
+             "allgather_ms_per_half_step": gath, "host_and_idle_ms_per_half_step": max(0.0, per_half - kern - gath),
+             "allgather_bytes_per_half_step": h * 10 * 8,
+             "items_per_gpu_per_half_step": 2 * n_loc, "resident_item_slots_per_gpu": slots}
+        d["limiter"] = ("kernel: one half-step cannot be shorter than the serial IAS15 integration of its longest leg (~8-9 ms for "
+                        "HD155358's 1244-step backward leg); %d items for %d resident slots per GPU"
+                        % (2 * n_loc, slots)) if kern > 4 * gath else "exchange"
+        out[label] = d
+        return theta, lnp, theta0
+
+    W_weak = 2 * slots * world                                  # two full waves of items per half-step and GPU
+    one(W_weak, "weak")
+    W_strong = 65536
+    theta, lnp, theta0 = one(W_strong, "strong")
+    # bit-identity: rank 0 repeats the strong-scaled ensemble on its own GPU (same seed, same steps: 1 warm-up + nsteps)
+    if rank == 0:
+        r = model.stretch_run(oh, theta0, nsteps + 1, seed=5, record_chain=False)
+        out["bit_identical_to_single_gpu"] = bool(np.array_equal(r["theta"], theta.cpu().numpy()))
+        t0 = time.perf_counter()
+        model.stretch_run(oh, theta0, nsteps, seed=5, record_chain=False)
+        one_gpu = W_strong * (nsteps + 1) / (time.perf_counter() - t0)
+        out["strong"]["single_gpu_evals_per_s"] = one_gpu
+        out["strong"]["speedup_vs_single_gpu"] = out["strong"]["evals_per_s"] / one_gpu
+    dist.barrier()
     return out
 
 
@@ -169,11 +335,20 @@ def main():
     ap.add_argument("--mapping", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=0, help="walkers in the timed CPU sample (0: about 15 s of work)")
-    ap.add_argument("--ess", action="store_true", help="also run the stretch / MH / SMALA samplers and report ESS/s")
+    ap.add_argument("--no-ess", action="store_true", help="skip the ESS/s block (three sampler runs, ~2 min)")
+    ap.add_argument("--ess", action="store_true", help="(default on; kept for compatibility)")
+    ap.add_argument("--ess-rows", type=int, default=2000, help="recorded rows (= sampler steps) per ESS run")
+    ap.add_argument("--no-var", action="store_true")
+    ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the sharded stretch block")
+    ap.add_argument("--sharded-steps", type=int, default=6)
+    ap.add_argument("--quick", action="store_true", help="smoke-sized side blocks (200 ESS rows, no CPU baseline)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
         return
+    if args.quick:
+        args.ess_rows = min(args.ess_rows, 200)
+        args.no_cpu_baseline = True
 
     import torch
     import torch.distributed as dist
@@ -268,8 +443,19 @@ def main():
         torch.cuda.synchronize()
     sampler.stop_flag = True
     sampler.join(timeout=2)
+
+    # ---- side blocks that every rank takes part in --------------------------------------------------------------
+    del flush
+    torch.cuda.empty_cache()
+    sharded = None
+    if world > 1 and not args.no_sharded:
+        sharded = run_stretch_sharded(ctx, model, oh, rank, world, dist, dev, torch, args.sharded_steps)
+    ess_block = None
+    if not args.no_ess:
+        ess_block = run_ess(ctx, model, oh, rank, world, dist if world > 1 else None, dev, args.ess_rows, torch)
     if rank != 0:
         if world > 1:
+            dist.barrier()
             dist.destroy_process_group()
         return
 
@@ -285,15 +471,17 @@ def main():
     kernel_ms = float(ms.mean())             # loglik kernel + finalize (finalize is ~us)
     achieved = flops_eval * W / (kernel_ms * 1e-3) / 1e12
     peak = ctx.fp64_peak_tflops()
+    prof = roofline_inputs()
+    lk = prof.get("loglik_kernel", {})
     roofline = {"bound": "fp64_fma_pipe", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": 5.33e6, "traffic_note": "dram bytes per launch, profiles/r01j_ncu_loglik_kernel.txt (algorithmic: %d B)" % (W * 92),
-                "executed_frac": 0.70,
+                "traffic": lk.get("dram_bytes_per_launch"),
+                "algorithmic_bytes_per_launch": W * 92,
+                "from_profile": {"file": "profiles/roofline_inputs.json", "loglik_kernel": lk, "fp64_peak_record": prof.get("fp64_peak")},
                 "executed_note": "frac uses SURVEY 8(d)'s ALGORITHMIC flop count (rebound's formulation); the kernel executes fewer "
                                  "FP64 instructions per decision (implicit star, coplanar, g-only corrector loop, no divisions), so frac can "
-                                 "exceed the pipe's real occupancy: ncu sm__pipe_fp64_cycles_active = 70%% of peak "
-                                 "(profiles/r01j_ncu_loglik_kernel.txt)",
+                                 "exceed the pipe's real occupancy: the ncu figure sm__pipe_fp64_cycles_active is from_profile.loglik_kernel",
                 "note": "achieved = SURVEY 8(d) algorithmic flops (S=%.0f force evals, T=%.0f step attempts per eval, "
-                        "432*S+1350*T) / CUDA-event kernel time; peak = dependent-free fma.rn.f64 microbenchmark on this GPU "
+                        "432*S+1350*T) / CUDA-event kernel time; peak = dependent-free fma.rn.f64 microbenchmark run now on this GPU "
                         "(rv_fp64_peak; MEASURED_PEAKS.json has no FP64 entry)" % (S_eval, T_eval)}
 
     # ---- the same evaluations under the two non-default epoch-handling options (never the headline value) ----
@@ -306,7 +494,7 @@ def main():
         model.set_option(key, 1)
         step_dev(0); torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        flush.zero_(); e0.record(); step_dev(0); e1.record(); torch.cuda.synchronize()
+        e0.record(); step_dev(0); e1.record(); torch.cuda.synchronize()
         okm = (d_status == 0)
         options[key] = {"value": W / (e0.elapsed_time(e1) * 1e-3), "unit": UNIT + " per GPU", "ms_per_step": e0.elapsed_time(e1),
                         "max_abs_logp_diff_vs_default": float((d_logp[okm] - ref_logp[okm]).abs().max().item()),
@@ -314,6 +502,10 @@ def main():
                                 "sequence)" % (key, note)}
         model.set_option(key, 0)
     step_dev(0); torch.cuda.synchronize()
+
+    var_block = None
+    if not args.no_var:
+        var_block = run_var(ctx, model, oh, dev, peak, torch)
 
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:        # a reported baseline: rank 0 at N = 1 only
@@ -349,10 +541,15 @@ def main():
     line["non_default_options"] = options
     if cpu_baseline:
         line["cpu_baseline"] = cpu_baseline
-    if args.ess and world == 1:
-        line["ess"] = run_ess(ctx, model, oh)
+    if ess_block is not None:
+        line["ess"] = ess_block
+    if var_block is not None:
+        line["var"] = var_block
+    if sharded is not None:
+        line["stretch_sharded"] = sharded
     print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

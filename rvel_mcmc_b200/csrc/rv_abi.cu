@@ -58,6 +58,7 @@ struct rv_model {
     rv::Model h;
     rv::Model* d;
     int mapping;
+    int var_layout;    // 0 automatic, 1 thread per (set, planet) -- see launch_var
 };
 
 static char g_err[512] = "";
@@ -202,7 +203,7 @@ int rv_model_create(rv_ctx* ctx, int n_planets, const double* fixed, int nvars, 
     if (!ctx || !out || !fixed) return fail(ctx, -1, "rv_model_create: NULL argument");
     rv_model* m = new (std::nothrow) rv_model();
     if (!m) return fail(ctx, -12, "out of host memory");
-    m->ctx = ctx; m->mapping = 0; m->d = nullptr;
+    m->ctx = ctx; m->mapping = 0; m->var_layout = 0; m->d = nullptr;
     const int rc = rv::build_model(&m->h, n_planets, fixed, nvars, free_planet, free_elem, hill_factor, dims);
     if (rc) {
         delete m;
@@ -232,6 +233,7 @@ int rv_model_set_option(rv_model* m, const char* key, double value) {
     else if (!strcmp(key, "max_attempts")) m->h.max_attempts = (int)value;
     else if (!strcmp(key, "hill_factor")) m->h.hill_factor = value;
     else if (!strcmp(key, "mapping")) m->mapping = (int)value;
+    else if (!strcmp(key, "var_layout")) m->var_layout = (int)value;
     else if (!strcmp(key, "check_prior")) m->h.check_prior = value != 0.0;
     else if (!strcmp(key, "monotone_backward")) m->h.monotone_backward = value != 0.0;
     else if (!strcmp(key, "dense_output")) m->h.dense_output = value != 0.0;
@@ -380,7 +382,8 @@ static int var_dev_impl(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, c
     const int nv = model->h.nvars;
     if (model->h.integrator != 0)
         return fail(ctx, -31, "the variational (gradient + Hessian) path integrates with IAS15 only; set integrator = 0");
-    if (rv::var_threads_needed(model->h.P, nv) > 448)
+    const bool set_per_lane = model->var_layout == 0 && model->h.P <= 2 && model->h.D == 2 && nv + 1 <= 32;
+    if (!set_per_lane && rv::var_threads_needed(model->h.P, nv) > 448)
         return fail(ctx, -30, "variational kernel: %d planets x %d free parameters need %d (set, planet) threads; the limit is 448",
                     model->h.P, nv, rv::var_threads_needed(model->h.P, nv));
     const int nsets = rv::var_nsets(nv);
@@ -395,7 +398,7 @@ static int var_dev_impl(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, c
     a.part = ctx->d_vpart; a.part_status = ctx->d_pstat;
     a.item_counter = ctx->d_item_counter;
     a.work_counters = ctx->count_work ? ctx->d_work : nullptr;
-    CU(ctx, rv::launch_var(a, model->h.P, model->h.D, nv, ctx->num_sms, s));
+    CU(ctx, rv::launch_var(a, model->h.P, model->h.D, nv, model->var_layout, ctx->num_sms, s));
     CU(ctx, rv::launch_var_finalize(ctx->d_vpart, ctx->d_pstat, W, nv, d_logp, d_grad, d_hess, d_status, ctx->d_item_counter, s));
     return 0;
 }

@@ -28,39 +28,55 @@ struct WalkerG : Walker<P, D, PL, VAR> {
     using B::t; using B::dt; using B::dt_last_done; using B::grp; using B::hist; using B::epsilon;
     using B::star_in_norm; using B::n_force; using B::n_attempt;
 
+    // One Gauss-Radau substep, software-pipelined: the only predictor term on the dependency chain is the one of the g
+    // coefficient the PREVIOUS substep has just updated (index kl); every other term was summed into pp while that substep's
+    // force evaluation was in flight.  Likewise the corrector's divided-difference sum over the older g (and a0) is formed
+    // before the force is known, so that g_{n-1} = fma(a_n, GA[n], sc) is one operation after it.  Same arithmetic as the
+    // straightforward form up to the order of summation.
+    //   pp[c]  in : ha0 + sum_{k != kl} PG[n][k] g_k         out: the same for the next substep (n % 7 + 1), without k = n - 1
     template <int n>
-    RV_D void substep_g(bool commit, const double (&x0c)[NC], double (&xp)[NC], double (&at)[NC], double (&dg6)[NC]) {
+    RV_D void substep_g(bool commit, const double (&x0c)[NC], double (&xp)[NC], double (&at)[NC], double (&dg6)[NC],
+                        double (&pp)[NC]) {
+        constexpr int kl = (n == 1) ? 6 : n - 2;
+        constexpr int m = (n % 7) + 1;
         const double dth = dt * tH<VAR>(n);
-        double xn[NC], an[NC];
+        double xn[NC], an[NC], sc[NC], ppn[NC];
 #pragma unroll
         for (int c = 0; c < NC; c++) {
-            double p0 = fma(tPG<VAR>(n, 0), b[0][c], ha0[c]);
-            p0 = fma(tPG<VAR>(n, 1), b[1][c], p0);
-            p0 = fma(tPG<VAR>(n, 2), b[2][c], p0);
-            double p1 = tPG<VAR>(n, 3) * b[3][c];
-            p1 = fma(tPG<VAR>(n, 4), b[4][c], p1);
-            p1 = fma(tPG<VAR>(n, 5), b[5][c], p1);
-            p1 = fma(tPG<VAR>(n, 6), b[6][c], p1);
-            const double inner = fma(dth, p0 + p1, v0[c]);
+            const double p = fma(tPG<VAR>(n, kl), b[kl][c], pp[c]);
+            const double inner = fma(dth, p, v0[c]);
             xn[c] = fma(dth, inner, x0c[c]);
         }
-        this->accel(xn, an);
+        // off the dependency chain of the force evaluation below
 #pragma unroll
         for (int c = 0; c < NC; c++) {
-            const double gk = an[c] - a0[c];
-            double s0 = gk * tGA<VAR>(n), s1 = 0.0;
+            double s0 = -a0[c] * tGA<VAR>(n), s1 = 0.0;
 #pragma unroll
             for (int i = 0; i < n - 1; i++) {
                 if (i & 1) s1 = fma(-b[i][c], tGB<VAR>(n, i), s1);
                 else s0 = fma(-b[i][c], tGB<VAR>(n, i), s0);
             }
-            const double gn = s0 + s1;
+            sc[c] = s0 + s1;
+            double q0 = ha0[c], q1 = 0.0;
+#pragma unroll
+            for (int k = 0; k < 7; k++) {
+                if (k == n - 1) continue;
+                if (k & 1) q1 = fma(tPG<VAR>(m, k), b[k][c], q1);
+                else q0 = fma(tPG<VAR>(m, k), b[k][c], q0);
+            }
+            ppn[c] = q0 + q1;
+        }
+        this->accel(xn, an);
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+            const double gn = fma(an[c], tGA<VAR>(n), sc[c]);
             if (n == 7) {
                 dg6[c] = sel(commit, gn - b[6][c], dg6[c]);
                 at[c] = sel(commit, an[c], at[c]);
                 xp[c] = sel(commit, xn[c], xp[c]);
             }
             b[n - 1][c] = sel(commit, gn, b[n - 1][c]);
+            pp[c] = ppn[c];
         }
     }
 
@@ -124,9 +140,19 @@ struct WalkerG : Walker<P, D, PL, VAR> {
                 b[j][c] = s + b[j][c];
             }
         }
-        double xp[NC], at[NC], dg6[NC];
+        double xp[NC], at[NC], dg6[NC], pp[NC];
 #pragma unroll
-        for (int c = 0; c < NC; c++) { xp[c] = x0[c]; at[c] = a0[c]; dg6[c] = 0.0; }
+        for (int c = 0; c < NC; c++) {
+            xp[c] = x0[c]; at[c] = a0[c]; dg6[c] = 0.0;
+            // predictor partial sum of substep 1: every term but g6's (see substep_g)
+            double q0 = ha0[c], q1 = 0.0;
+#pragma unroll
+            for (int k = 0; k < 6; k++) {
+                if (k & 1) q1 = fma(tPG<VAR>(1, k), b[k][c], q1);
+                else q0 = fma(tPG<VAR>(1, k), b[k][c], q0);
+            }
+            pp[c] = q0 + q1;
+        }
         Ratio pc_err{1e300, 1.0}, pc_last{2.0, 1.0};
         int it = 0;
         bool iterating = active;
@@ -134,13 +160,13 @@ struct WalkerG : Walker<P, D, PL, VAR> {
             if (iterating && (ratio_lt(pc_err, 1e-16) || (it > 2 && ratio_le(pc_last, pc_err)) || it >= 12)) iterating = false;
             if (!warp_any(iterating)) break;
             if (iterating) { pc_last = pc_err; it++; }
-            substep_g<1>(iterating, x0c, xp, at, dg6);
-            substep_g<2>(iterating, x0c, xp, at, dg6);
-            substep_g<3>(iterating, x0c, xp, at, dg6);
-            substep_g<4>(iterating, x0c, xp, at, dg6);
-            substep_g<5>(iterating, x0c, xp, at, dg6);
-            substep_g<6>(iterating, x0c, xp, at, dg6);
-            substep_g<7>(iterating, x0c, xp, at, dg6);
+            substep_g<1>(iterating, x0c, xp, at, dg6, pp);
+            substep_g<2>(iterating, x0c, xp, at, dg6, pp);
+            substep_g<3>(iterating, x0c, xp, at, dg6, pp);
+            substep_g<4>(iterating, x0c, xp, at, dg6, pp);
+            substep_g<5>(iterating, x0c, xp, at, dg6, pp);
+            substep_g<6>(iterating, x0c, xp, at, dg6, pp);
+            substep_g<7>(iterating, x0c, xp, at, dg6, pp);
             double maxdg = 0.0, maxat = 0.0;
 #pragma unroll
             for (int c = 0; c < NC; c++) {

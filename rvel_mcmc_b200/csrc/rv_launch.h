@@ -14,7 +14,7 @@ cudaError_t launch_fp64_peak(double* d_out, int blocks, int iters, cudaStream_t 
 // variational path (rv_var_kernels.cu)
 struct VarArgs;
 int var_threads_needed(int P, int nv);
-cudaError_t launch_var(const VarArgs& a, int P, int D, int nv, int num_sms, cudaStream_t stream);
+cudaError_t launch_var(const VarArgs& a, int P, int D, int nv, int layout, int num_sms, cudaStream_t stream);
 cudaError_t launch_var_finalize(const double* part, const int* pstat, long long W, int nv, double* logp, double* grad,
                                 double* hess, int* status, unsigned long long* item_counter, cudaStream_t stream);
 // optional WHFast variant (rv_whfast_kernels.cu)

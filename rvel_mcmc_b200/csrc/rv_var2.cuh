@@ -1,0 +1,715 @@
+// rv_var2.cuh -- value + gradient + Hessian of the RV log-likelihood, "one lane per variational set" layout.
+//
+// Same contract as rv_var.cuh (State.get_logp_d_dd, state.py:290-294; setup_sim_vars state.py:229-248; get_chi2_d_dd
+// state.py:253-285; one CTA per (walker, leg), all sets share one IAS15 step sequence, real-only step-size norm), but a
+// different mapping for systems of one or two planets:
+//   * every lane owns a whole variational SET -- all P planets of it -- so a second-order lane needs nothing from the
+//     other second-order lanes: pair terms are computed once (Newton's third law), its own predicted positions never
+//     leave its registers;
+//   * the real set and the nv first-order sets ("cheap" sets) live in ONE producer warp.  They do not depend on the
+//     second-order sets, so that warp runs ahead inside a predictor-corrector iteration: per Gauss-Radau substep it
+//     publishes its predicted positions and star sums to shared memory and signals a NAMED barrier (bar.arrive); the
+//     second-order warps wait on that barrier only (bar.sync) -- no CTA-wide barrier per substep;
+//   * the only CTA-wide barriers are the convergence monitor (once per iteration) and the once-per-step bookkeeping.
+// The once-per-step state (x0, carries, e, and the rejected-step history br / er) lives in shared memory, strided per lane.
+// Written against an executor like rv_var.cuh, so the CPU test-suite runs the same source sequentially.
+#pragma once
+#include "rv_var.cuh"
+
+namespace rv {
+
+struct Var2Layout {
+    int P, D, nv, n2, nsets;
+    int nso_warps;     // warps of second-order lanes (lane t of these warps owns second-order set t)
+    int NT;            // threads launched = 32 * (nso_warps + 1); the last warp is the producer (real + first-order)
+    int nslots;        // lanes that own a set: n2 + nv + 1 (slot = t for second-order, n2 + lane for the producer warp)
+    int CB;            // doubles per cheap-set block in a buffer: P*D positions + D star sum
+    int cstride;       // doubles per buffer: (nv + 1) * CB
+    int o_cbuf, o_vx, o_dm, o_red, o_real, o_state, total;   // offsets in doubles
+};
+constexpr int VAR2_STATE_PER_COORD = 24;   // x0, csx, csv, e[7], br[7], er[7]
+
+// NT = 0: the smallest CTA that fits; otherwise the launched size (a multiple of 32, at least var2_min_threads)
+RV_HD int var2_min_threads(int nv) { return 32 * ((nv * (nv + 1) / 2 + 31) / 32 + 1); }
+RV_HD Var2Layout var2_layout(int P, int D, int nv, int NT = 0) {
+    Var2Layout L;
+    L.P = P; L.D = D; L.nv = nv; L.n2 = nv * (nv + 1) / 2; L.nsets = 1 + nv + L.n2;
+    L.NT = NT > 0 ? NT : var2_min_threads(nv);
+    L.nso_warps = L.NT / 32 - 1;
+    L.nslots = L.n2 + nv + 1;
+    L.CB = P * D + D;
+    L.cstride = (nv + 1) * L.CB;
+    if (L.cstride & 1) L.cstride++;
+    int o = 0;
+    L.o_cbuf = o; o += 8 * L.cstride;                       // buffer 0: positions at x0; 1..7: predicted at substep n
+    L.o_vx = o; o += L.nsets * P; if (o & 1) o++;
+    L.o_dm = o; o += (nv > 0 ? nv : 1) * P; if (o & 1) o++;
+    L.o_red = o; o += 2 * 2 * 32 + 2;
+    L.o_real = o; o += 2 * P * D; if (o & 1) o++;           // the real lane's last force and b6 (step-size control)
+    L.o_state = o; o += VAR2_STATE_PER_COORD * P * D * L.nslots;
+    L.total = o;
+    return L;
+}
+RV_HD bool var2_supported(int P, int nv) { return P <= 2 && nv + 1 <= 32; }
+
+template <int P, int D>
+struct Var2Thread {
+    static constexpr int NC = P * D;
+    int tid, role;                 // role: 0 real, 1 first-order, 2 second-order, -1 idle
+    int set, slot, pa, pb;
+    int ou, oa, ob;                // block offsets inside a cheap buffer: own (producer lanes), parents (second-order)
+    double x0c[NC], v0[NC], a0[NC], ha0[NC];
+    double q[7][NC];               // b between step attempts, g inside the predictor-corrector loop
+    double xn[NC];
+    double mon_g, mon_a;           // convergence-monitor contributions of the last substep-7
+    double acc;                    // running chi2 / d[a] / dd[a][b]
+};
+
+template <int P, int D>
+RV_D void var2_assign(Var2Thread<P, D>& th, int tid, const Var2Layout& L) {
+    th.tid = tid; th.role = -1; th.set = 0; th.slot = 0; th.pa = th.pb = 0;
+    const int warp = tid >> 5, lane = tid & 31;
+    if (warp < L.nso_warps) {
+        if (tid < L.n2) {
+            th.role = 2; th.set = 1 + L.nv + tid; th.slot = tid;
+            int a = 0;
+            while ((a + 1) * (a + 2) / 2 <= tid) a++;
+            th.pa = a; th.pb = tid - a * (a + 1) / 2;
+        }
+    } else if (lane <= L.nv) {
+        th.role = lane == 0 ? 0 : 1; th.set = lane; th.slot = L.n2 + lane;
+        th.pa = th.pb = lane == 0 ? 0 : lane - 1;
+    }
+    th.ou = th.set * L.CB;
+    th.oa = (1 + th.pa) * L.CB; th.ob = (1 + th.pb) * L.CB;
+}
+
+// ---- forces ------------------------------------------------------------------------------------------------------
+// real set: a_i = -m0 f(x_i + S) - sum_{j != i} m_j f(x_i - x_j), f(d) = d / r^3, S = sum mu_j x_j (= -r_star)
+template <int P, int D>
+RV_D void var2_force_real(const double (&x)[P * D], const double (&S)[D], const VarUniform<P>& u, double (&an)[P * D]) {
+#pragma unroll
+    for (int i = 0; i < P; i++) {
+        double ds[D], r2 = 0.0;
+#pragma unroll
+        for (int d = 0; d < D; d++) { ds[d] = x[i * D + d] + S[d]; r2 = fma(ds[d], ds[d], r2); }
+        const double y = rinv1(r2);
+        const double k = -u.gm0 * (y * y * y);
+#pragma unroll
+        for (int d = 0; d < D; d++) an[i * D + d] = k * ds[d];
+    }
+#pragma unroll
+    for (int i = 0; i < P; i++)
+#pragma unroll
+        for (int j = i + 1; j < P; j++) {
+            double dp[D], r2 = 0.0;
+#pragma unroll
+            for (int d = 0; d < D; d++) { dp[d] = x[i * D + d] - x[j * D + d]; r2 = fma(dp[d], dp[d], r2); }
+            const double y = rinv1(r2), r3 = y * y * y;
+            const double ki = -u.gm[j] * r3, kj = u.gm[i] * r3;
+#pragma unroll
+            for (int d = 0; d < D; d++) {
+                an[i * D + d] = fma(ki, dp[d], an[i * D + d]);
+                an[j * D + d] = fma(kj, dp[d], an[j * D + d]);
+            }
+        }
+}
+
+// first-order set U with mass variations dmu[j] (= d mu_j):  da_i = -sum_j { m_j Df[U_ij] + dm_j f(d_ij) },
+// Df[u] = u / r^3 - 3 d (d.u) / r^5; star terms with d = x0_i + S, u = xu_i + SU, dm_star = 0
+template <int P, int D>
+RV_D void var2_force_first(const double (&xu)[P * D], const double* __restrict__ X0, const double (&S)[D],
+                           const double (&SU)[D], const double* __restrict__ dmu, const VarUniform<P>& u,
+                           double (&an)[P * D]) {
+    double x0[P][D];
+#pragma unroll
+    for (int i = 0; i < P; i++)
+#pragma unroll
+        for (int d = 0; d < D; d++) x0[i][d] = X0[i * D + d];
+#pragma unroll
+    for (int i = 0; i < P; i++) {
+        double dd[D], U[D], r2 = 0.0, du = 0.0;
+#pragma unroll
+        for (int d = 0; d < D; d++) {
+            dd[d] = x0[i][d] + S[d]; U[d] = xu[i * D + d] + SU[d];
+            r2 = fma(dd[d], dd[d], r2); du = fma(dd[d], U[d], du);
+        }
+        const double y = rinv1(r2), y2 = y * y, r3i = y * y2, r5i = r3i * y2;
+        const double kU = -u.gm0 * r3i, kd = u.gm0 * 3.0 * r5i * du;
+#pragma unroll
+        for (int d = 0; d < D; d++) an[i * D + d] = fma(kU, U[d], kd * dd[d]);
+    }
+#pragma unroll
+    for (int i = 0; i < P; i++)
+#pragma unroll
+        for (int j = i + 1; j < P; j++) {
+            double dd[D], U[D], r2 = 0.0, du = 0.0;
+#pragma unroll
+            for (int d = 0; d < D; d++) {
+                dd[d] = x0[i][d] - x0[j][d]; U[d] = xu[i * D + d] - xu[j * D + d];
+                r2 = fma(dd[d], dd[d], r2); du = fma(dd[d], U[d], du);
+            }
+            const double y = rinv1(r2), y2 = y * y, r3i = y * y2, r5i = r3i * y2;
+            const double c5du = -3.0 * r5i * du;
+            // side i uses (m_j, dm_j), side j uses (m_i, dm_i) with the opposite sign
+            const double kUi = u.gm[j] * r3i, kdi = fma(u.gm[j], c5du, dmu[j] * u.gm0 * r3i);
+            const double kUj = u.gm[i] * r3i, kdj = fma(u.gm[i], c5du, dmu[i] * u.gm0 * r3i);
+#pragma unroll
+            for (int d = 0; d < D; d++) {
+                an[i * D + d] -= fma(kUi, U[d], kdi * dd[d]);
+                an[j * D + d] += fma(kUj, U[d], kdj * dd[d]);
+            }
+        }
+}
+
+// second-order set U with parents A, B:  d2a_i = -sum_j { m_j (Df[U] + D2f[A,B]) + dm_j^a Df[B] + dm_j^b Df[A] },
+// D2f[u,w] = -3 [u (d.w) + w (d.u) + d (u.w)] / r^5 + 15 d (d.u)(d.w) / r^7          (d2 m = 0)
+template <int P, int D>
+RV_D void var2_force_second(const double (&xu)[P * D], const double* __restrict__ X0, const double* __restrict__ XA,
+                            const double* __restrict__ XB, const double* __restrict__ dma, const double* __restrict__ dmb,
+                            const VarUniform<P>& u, double (&an)[P * D]) {
+    double x0[P][D], xa[P][D], xb[P][D], S[D], SA[D], SB[D], SU[D];
+#pragma unroll
+    for (int i = 0; i < P; i++)
+#pragma unroll
+        for (int d = 0; d < D; d++) { x0[i][d] = X0[i * D + d]; xa[i][d] = XA[i * D + d]; xb[i][d] = XB[i * D + d]; }
+#pragma unroll
+    for (int d = 0; d < D; d++) {
+        S[d] = X0[P * D + d]; SA[d] = XA[P * D + d]; SB[d] = XB[P * D + d];
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < P; j++) s = fma(u.mu[j], xu[j * D + d], fma(dma[j], xb[j][d], fma(dmb[j], xa[j][d], s)));
+        SU[d] = s;
+    }
+    // star pairs (dm_star = 0)
+#pragma unroll
+    for (int i = 0; i < P; i++) {
+        double dd[D], A[D], B[D], U[D], r2 = 0.0, da = 0.0, db = 0.0, ab = 0.0, du = 0.0;
+#pragma unroll
+        for (int d = 0; d < D; d++) {
+            dd[d] = x0[i][d] + S[d]; A[d] = xa[i][d] + SA[d]; B[d] = xb[i][d] + SB[d]; U[d] = xu[i * D + d] + SU[d];
+            r2 = fma(dd[d], dd[d], r2); da = fma(dd[d], A[d], da); db = fma(dd[d], B[d], db);
+            ab = fma(A[d], B[d], ab); du = fma(dd[d], U[d], du);
+        }
+        const double y = rinv1(r2), y2 = y * y, r3i = y * y2, r5i = r3i * y2, r7i = r5i * y2;
+        const double c5 = -3.0 * r5i;
+        const double m = u.gm0;
+        const double kU = m * r3i, kA = m * c5 * db, kB = m * c5 * da;
+        const double kd = m * fma(c5, du + ab, 15.0 * r7i * (da * db));
+#pragma unroll
+        for (int d = 0; d < D; d++) an[i * D + d] = -fma(kU, U[d], fma(kA, A[d], fma(kB, B[d], kd * dd[d])));
+    }
+    // planet pairs, both sides from one set of geometric scalars
+#pragma unroll
+    for (int i = 0; i < P; i++)
+#pragma unroll
+        for (int j = i + 1; j < P; j++) {
+            double dd[D], A[D], B[D], U[D], r2 = 0.0, da = 0.0, db = 0.0, ab = 0.0, du = 0.0;
+#pragma unroll
+            for (int d = 0; d < D; d++) {
+                dd[d] = x0[i][d] - x0[j][d]; A[d] = xa[i][d] - xa[j][d]; B[d] = xb[i][d] - xb[j][d];
+                U[d] = xu[i * D + d] - xu[j * D + d];
+                r2 = fma(dd[d], dd[d], r2); da = fma(dd[d], A[d], da); db = fma(dd[d], B[d], db);
+                ab = fma(A[d], B[d], ab); du = fma(dd[d], U[d], du);
+            }
+            const double y = rinv1(r2), y2 = y * y, r3i = y * y2, r5i = r3i * y2, r7i = r5i * y2;
+            const double c5 = -3.0 * r5i;
+            const double g0 = fma(c5, du + ab, 15.0 * r7i * (da * db));   // coefficient of m d
+            const double c5db = c5 * db, c5da = c5 * da;
+            const double dgaj = dma[j] * u.gm0, dgbj = dmb[j] * u.gm0, dgai = dma[i] * u.gm0, dgbi = dmb[i] * u.gm0;
+            {   // side i: masses of j
+                const double m = u.gm[j];
+                const double kU = m * r3i, kA = fma(m, c5db, dgbj * r3i), kB = fma(m, c5da, dgaj * r3i);
+                const double kd = fma(m, g0, fma(dgaj, c5db, dgbj * c5da));
+#pragma unroll
+                for (int d = 0; d < D; d++) an[i * D + d] -= fma(kU, U[d], fma(kA, A[d], fma(kB, B[d], kd * dd[d])));
+            }
+            {   // side j: masses of i, opposite sign
+                const double m = u.gm[i];
+                const double kU = m * r3i, kA = fma(m, c5db, dgbi * r3i), kB = fma(m, c5da, dgai * r3i);
+                const double kd = fma(m, g0, fma(dgai, c5db, dgbi * c5da));
+#pragma unroll
+                for (int d = 0; d < D; d++) an[j * D + d] += fma(kU, U[d], fma(kA, A[d], fma(kB, B[d], kd * dd[d])));
+            }
+        }
+}
+
+// ---- predictor / corrector over the lane's NC coordinates ----------------------------------------------------------
+template <int P, int D>
+RV_D void var2_predict_positions(Var2Thread<P, D>& th, int n, double dt) {
+    constexpr int NC = P * D;
+    const double dth = dt * rvtabm::H[n];
+    const double c0 = rvtabm::PG[n][0], c1 = rvtabm::PG[n][1], c2 = rvtabm::PG[n][2], c3 = rvtabm::PG[n][3],
+                 c4 = rvtabm::PG[n][4], c5 = rvtabm::PG[n][5], c6 = rvtabm::PG[n][6];
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+        double p0 = fma(c0, th.q[0][c], th.ha0[c]);
+        p0 = fma(c1, th.q[1][c], p0);
+        p0 = fma(c2, th.q[2][c], p0);
+        double p1 = c3 * th.q[3][c];
+        p1 = fma(c4, th.q[4][c], p1);
+        p1 = fma(c5, th.q[5][c], p1);
+        p1 = fma(c6, th.q[6][c], p1);
+        const double inner = fma(dth, p0 + p1, th.v0[c]);
+        th.xn[c] = fma(dth, inner, th.x0c[c]);
+    }
+}
+
+template <int n, int P, int D>
+RV_D void var2_corrector_n(Var2Thread<P, D>& th, const double (&an)[P * D]) {
+    constexpr int NC = P * D;
+    double mg = 0.0, ma = 0.0;
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+        const double gk = an[c] - th.a0[c];
+        double s0 = gk * rvtab::GA[n], s1 = 0.0;
+#pragma unroll
+        for (int i = 0; i < n - 1; i++) {
+            if (i & 1) s1 = fma(-th.q[i][c], rvtab::GB[n][i], s1);
+            else s0 = fma(-th.q[i][c], rvtab::GB[n][i], s0);
+        }
+        const double gn = s0 + s1;
+        if (n == 7) {
+            const double ak = fabs(an[c]), dg = fabs(gn - th.q[6][c]);
+            if (is_normal(ak) && ak > ma) ma = ak;
+            if (is_normal(dg) && dg > mg) mg = dg;
+        }
+        th.q[n - 1][c] = gn;
+    }
+    if (n == 7) { th.mon_g = mg; th.mon_a = ma; }
+}
+template <int P, int D>
+RV_D void var2_corrector(Var2Thread<P, D>& th, int n, const double (&an)[P * D]) {
+    switch (n) {
+        case 1: var2_corrector_n<1>(th, an); break;
+        case 2: var2_corrector_n<2>(th, an); break;
+        case 3: var2_corrector_n<3>(th, an); break;
+        case 4: var2_corrector_n<4>(th, an); break;
+        case 5: var2_corrector_n<5>(th, an); break;
+        case 6: var2_corrector_n<6>(th, an); break;
+        default: var2_corrector_n<7>(th, an); break;
+    }
+}
+
+// Initial conditions of every planet of the lane's set: the jet of the barycentric state with respect to the set's
+// parameters (state.py:229-248: add_variation + vary + move_to_com).
+template <int P, int D>
+RV_D void var2_initial(const Var2Thread<P, D>& th, const Model* __restrict__ md, const double (&el)[P][NELEM],
+                       double (&x0)[P * D], double (&v0)[P * D]) {
+    const double m0 = md->m_star;
+    Jet mt = J(m0), cx[3], cv[3];
+#pragma unroll
+    for (int d = 0; d < 3; d++) { cx[d] = J(0.0); cv[d] = J(0.0); }
+    JState own[P];
+    for (int i = 0; i < P; i++) {
+        Jet ej[NELEM];
+#pragma unroll
+        for (int k = 0; k < NELEM; k++) ej[k] = J(el[i][k]);
+        if (th.role >= 1 && md->free_planet[th.pa] == i) ej[md->free_elem[th.pa]].d1 = 1.0;
+        if (th.role == 2 && md->free_planet[th.pb] == i) ej[md->free_elem[th.pb]].d2 = 1.0;
+        const JState s = pal_to_cart_jet(ej, m0);
+        mt = mt + s.m;
+#pragma unroll
+        for (int d = 0; d < 3; d++) { cx[d] = cx[d] + s.m * s.x[d]; cv[d] = cv[d] + s.m * s.v[d]; }
+        own[i] = s;
+    }
+    const Jet im = jinv(mt);
+#pragma unroll
+    for (int i = 0; i < P; i++)
+#pragma unroll
+        for (int d = 0; d < D; d++) {
+            const Jet x = own[i].x[d] - cx[d] * im, v = own[i].v[d] - cv[d] * im;
+            x0[i * D + d] = th.role == 0 ? x.v : (th.role == 1 ? x.d1 : x.d12);
+            v0[i * D + d] = th.role == 0 ? v.v : (th.role == 1 ? v.d1 : v.d12);
+        }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// The CTA algorithm.  Exec provides (device / sequential host emulation):
+//   each(f)            run f(Var2Thread&) for every thread of the CTA
+//   sync()             CTA barrier
+//   producer_sync()    barrier among the lanes of the producer warp (no-op for the others)
+//   signal(n)          producer warp: arrive on named barrier n (after publishing substep n)
+//   wait(n)            second-order warps: wait on named barrier n
+//   stage_max / read_max / fetch / add_work   as in rv_var.cuh
+template <int P, int D, class Exec>
+RV_D void var2_run_items(Exec& ex, const VarArgs& a, const Var2Layout& L, double* __restrict__ sm) {
+    constexpr int NC = P * D;
+    constexpr int SPC = VAR2_STATE_PER_COORD;
+    const Model* __restrict__ md = a.model;
+    const int nv = md->nvars;
+    const int NS = L.nslots;
+    double* const cbuf = sm + L.o_cbuf;
+    double* const vxs = sm + L.o_vx;
+    double* const dm = sm + L.o_dm;
+    double* const realv = sm + L.o_real;
+    double* const state = sm + L.o_state;
+    const double m0 = md->m_star;
+    const long long n_items = 2 * a.W;
+    VarUniform<P> u;
+    u.gm0 = m0;
+    u.epsilon = md->epsilon;
+    // per-lane state in shared memory: entry k of coordinate c at state[(k * NC + c) * NS + slot]
+    auto ST = [&](const Var2Thread<P, D>& th, int k, int c) -> double& { return state[(size_t)(k * NC + c) * NS + th.slot]; };
+    enum { K_X0 = 0, K_CSX = 1, K_CSV = 2, K_E = 3, K_BR = 10, K_ER = 17 };
+
+    ex.each([&](Var2Thread<P, D>& th) {
+        if (th.tid < nv * P) {
+            const int q = th.tid / P, j = th.tid - q * P;
+            dm[th.tid] = (md->free_planet[q] == j && md->free_elem[q] == EL_M) ? 1.0 / m0 : 0.0;
+        }
+    });
+
+    for (;;) {
+        const long long item = ex.fetch(a.item_counter);
+        if (item >= n_items) break;
+        const bool backward = item < a.W;
+        const long long wi = backward ? item : item - a.W;
+        const int n = backward ? a.nb : a.nf;
+        const int base = backward ? a.nf : 0;
+        double el[P][NELEM];
+        bool bad = false;
+        double hill = 0.0;
+#pragma unroll
+        for (int i = 0; i < P; i++) {
+#pragma unroll
+            for (int k = 0; k < NELEM; k++) {
+                const int s = md->src[i * NELEM + k];
+                el[i][k] = (s >= 0) ? a.theta[wi * nv + s] : md->fixed[i * NELEM + k];
+            }
+            bad = bad || prior_hard(el[i]);
+            u.gm[i] = el[i][EL_M];
+            u.mu[i] = el[i][EL_M] / m0;
+        }
+        int final_status = -1;
+        unsigned long long n_force = 0, n_attempt = 0;
+        if (bad && a.check_prior) final_status = ST_PRIOR;
+        if (final_status < 0) {
+#pragma unroll
+            for (int i = 0; i < P; i++) {
+                const double rh = el[i][EL_A] * pow(el[i][EL_M] / (3.0 * m0), 1.0 / 3.0);
+                if (rh > hill) hill = rh;
+            }
+            const double emd = md->hill_factor * hill;
+            u.min2 = emd * emd;
+
+            // publish the producer lanes' positions x (and star sums) into buffer `b`: two phases around a producer-warp sync
+            auto publish_positions = [&](int b, bool from_xn) {
+                double* Xw = cbuf + b * L.cstride;
+                ex.each([&](Var2Thread<P, D>& th) {
+                    if (th.role != 0 && th.role != 1) return;
+                    double* blk = Xw + th.ou;
+#pragma unroll
+                    for (int c = 0; c < NC; c++) blk[c] = from_xn ? th.xn[c] : ST(th, K_X0, c);
+                    if (th.role == 0) {
+#pragma unroll
+                        for (int d = 0; d < D; d++) {
+                            double s = 0.0;
+#pragma unroll
+                            for (int j = 0; j < P; j++) s = fma(u.mu[j], blk[j * D + d], s);
+                            blk[NC + d] = s;
+                        }
+                    }
+                });
+                ex.producer_sync();
+                ex.each([&](Var2Thread<P, D>& th) {
+                    if (th.role != 1) return;
+                    double* blk = Xw + th.ou;
+                    const double* dma = dm + th.pa * P;
+#pragma unroll
+                    for (int d = 0; d < D; d++) {
+                        double s = 0.0;
+#pragma unroll
+                        for (int j = 0; j < P; j++) s = fma(u.mu[j], blk[j * D + d], fma(dma[j], Xw[j * D + d], s));
+                        blk[NC + d] = s;
+                    }
+                });
+            };
+            // force on the lane's set at positions x (own) with the producer data of buffer b
+            auto force = [&](const Var2Thread<P, D>& th, int b, const double (&x)[NC], double (&an)[NC]) {
+                const double* Xr = cbuf + b * L.cstride;
+                if (th.role == 2) {
+                    var2_force_second<P, D>(x, Xr, Xr + th.oa, Xr + th.ob, dm + th.pa * P, dm + th.pb * P, u, an);
+                } else if (th.role == 1) {
+                    double S[D], SU[D];
+#pragma unroll
+                    for (int d = 0; d < D; d++) { S[d] = Xr[NC + d]; SU[d] = Xr[th.ou + NC + d]; }
+                    var2_force_first<P, D>(x, Xr, S, SU, dm + th.pa * P, u, an);
+                } else {
+                    double S[D];
+#pragma unroll
+                    for (int d = 0; d < D; d++) S[d] = Xr[NC + d];
+                    var2_force_real<P, D>(x, S, u, an);
+                }
+            };
+
+            ex.each([&](Var2Thread<P, D>& th) {
+                if (th.role < 0) return;
+                double x0[NC], v0[NC];
+                var2_initial(th, md, el, x0, v0);
+                th.acc = 0.0; th.mon_g = 0.0; th.mon_a = 0.0;
+#pragma unroll
+                for (int c = 0; c < NC; c++) {
+                    th.v0[c] = v0[c]; th.a0[c] = 0.0; th.ha0[c] = 0.0; th.xn[c] = x0[c]; th.x0c[c] = x0[c];
+                    ST(th, K_X0, c) = x0[c]; ST(th, K_CSX, c) = 0.0; ST(th, K_CSV, c) = 0.0;
+#pragma unroll
+                    for (int k = 0; k < 7; k++) {
+                        th.q[k][c] = 0.0;
+                        ST(th, K_E + k, c) = 0.0; ST(th, K_BR + k, c) = 0.0; ST(th, K_ER + k, c) = 0.0;
+                    }
+                }
+            });
+            publish_positions(0, false);
+            ex.sync();
+
+            VarClock w;
+            w.t = 0.0; w.dt = md->dt0; w.dt_last_done = 0.0;
+            LegCursor c;
+            c.status = RUN; c.ie = 0; c.n = n; c.attempts = 0; c.tmax = 0.0; c.last_full_dt = 0.0; c.chi2 = 0.0;
+
+            // ---- one IAS15 step attempt of the whole CTA; bit0 accepted, bit1 encounter after the step ----
+            auto attempt = [&]() -> int {
+                n_attempt++;
+                ex.each([&](Var2Thread<P, D>& th) {
+                    if (th.role < 0) return;
+                    double x0[NC];
+#pragma unroll
+                    for (int cc = 0; cc < NC; cc++) x0[cc] = ST(th, K_X0, cc);
+                    force(th, 0, x0, th.a0);
+#pragma unroll
+                    for (int cc = 0; cc < NC; cc++) {
+                        th.ha0[cc] = 0.5 * th.a0[cc];
+                        th.x0c[cc] = x0[cc] - ST(th, K_CSX, cc);
+#pragma unroll
+                        for (int j = 0; j < 7; j++) {      // g from b, in place
+                            double s = 0.0;
+#pragma unroll
+                            for (int k = 6; k > j; k--) s = fma(th.q[k][cc], rvtab::DD[k][j], s);
+                            th.q[j][cc] = s + th.q[j][cc];
+                        }
+                    }
+                });
+                Ratio pc_err{1e300, 1.0}, pc_last{2.0, 1.0};
+                int it = 0;
+                const double dt = w.dt;
+                while (true) {
+                    if (ratio_lt(pc_err, 1e-16) || (it > 2 && ratio_le(pc_last, pc_err)) || it >= 12) break;
+                    pc_last = pc_err;
+                    it++;
+#pragma unroll 1
+                    for (int nn = 1; nn <= 7; nn++) {
+                        // producer warp: predict, publish, signal, then its own force + corrector
+                        ex.each([&](Var2Thread<P, D>& th) { if (th.role == 0 || th.role == 1) var2_predict_positions(th, nn, dt); });
+                        publish_positions(nn, true);
+                        ex.signal(nn);
+                        ex.each([&](Var2Thread<P, D>& th) {
+                            if (th.role != 0 && th.role != 1) return;
+                            double an[NC];
+                            force(th, nn, th.xn, an);
+                            var2_corrector(th, nn, an);
+                            if (nn == 7 && th.role == 0) {
+#pragma unroll
+                                for (int cc = 0; cc < NC; cc++) realv[cc] = an[cc];
+                            }
+                        });
+                        // second-order warps: predict in registers, wait for the producer's substep, force + corrector
+                        ex.each([&](Var2Thread<P, D>& th) { if (th.role == 2) var2_predict_positions(th, nn, dt); });
+                        ex.wait(nn);
+                        ex.each([&](Var2Thread<P, D>& th) {
+                            if (th.role != 2) return;
+                            double an[NC];
+                            force(th, nn, th.xn, an);
+                            var2_corrector(th, nn, an);
+                        });
+                    }
+                    ex.each([&](Var2Thread<P, D>& th) {
+                        ex.stage_max(th, th.role >= 0 ? th.mon_g : 0.0, th.role >= 0 ? th.mon_a : 0.0);
+                    });
+                    ex.sync();
+                    double maxdg, maxat;
+                    ex.read_max(maxdg, maxat);
+                    pc_err.num = maxdg; pc_err.den = maxat;
+                    n_force += 7;
+                }
+                n_force += 1;
+                // b from g, in place; then step-size control over the real particles
+                ex.each([&](Var2Thread<P, D>& th) {
+                    double mb = 0.0, ma = 0.0;
+                    if (th.role >= 0) {
+#pragma unroll
+                        for (int cc = 0; cc < NC; cc++) {
+#pragma unroll
+                            for (int k = 0; k < 7; k++) {
+                                double s = 0.0;
+#pragma unroll
+                                for (int j = 6; j > k; j--) s = fma(th.q[j][cc], rvtab::CC[j][k], s);
+                                th.q[k][cc] = s + th.q[k][cc];
+                            }
+                        }
+                    }
+                    if (th.role == 0) {
+#pragma unroll
+                        for (int p = 0; p < P; p++) {
+                            double v2 = 0.0, x2 = 0.0;
+#pragma unroll
+                            for (int d = 0; d < D; d++) {
+                                v2 = fma(th.v0[p * D + d], th.v0[p * D + d], v2); x2 = fma(th.xn[p * D + d], th.xn[p * D + d], x2);
+                            }
+                            const bool keep = !(fabs(v2 * dt * dt) < 1e-16 * x2);
+#pragma unroll
+                            for (int d = 0; d < D; d++) {
+                                const double ak = fabs(realv[p * D + d]), b6 = fabs(th.q[6][p * D + d]);
+                                if (keep && is_normal(ak) && ak > ma) ma = ak;
+                                if (keep && is_normal(b6) && b6 > mb) mb = b6;
+                            }
+                        }
+                    }
+                    ex.stage_max(th, mb, ma);
+                });
+                ex.sync();
+                double maxb6, maxak;
+                ex.read_max(maxb6, maxak);
+                const double err = maxb6 / maxak;
+                const double dt_done = dt;
+                double dt_new;
+                if (is_normal(err)) dt_new = inv_root7(err / u.epsilon) * dt_done;
+                else dt_new = dt_done * 4.0;
+                int result = 0;
+                if (fabs(dt_new) < 0.25 * fabs(dt_done)) {
+                    w.dt = dt_new;
+                    if (w.dt_last_done != 0.0) {
+                        const double q = w.dt / w.dt_last_done;
+                        ex.each([&](Var2Thread<P, D>& th) {
+                            if (th.role < 0) return;
+#pragma unroll
+                            for (int cc = 0; cc < NC; cc++) {
+                                double _e[7], _b[7], e[7];
+#pragma unroll
+                                for (int k = 0; k < 7; k++) { _e[k] = ST(th, K_ER + k, cc); _b[k] = ST(th, K_BR + k, cc); }
+                                var_predict<NC>(q, _e, _b, e, th.q, cc);
+#pragma unroll
+                                for (int k = 0; k < 7; k++) ST(th, K_E + k, cc) = e[k];
+                            }
+                        });
+                    }
+                } else {
+                    if (fabs(dt_new) > 4.0 * fabs(dt_done)) dt_new = dt_done * 4.0;
+                    w.dt = dt_new;
+                    const double dt2 = dt_done * dt_done;
+                    const double q = w.dt / dt_done;
+                    ex.each([&](Var2Thread<P, D>& th) {
+                        if (th.role < 0) return;
+#pragma unroll
+                        for (int cc = 0; cc < NC; cc++) {
+                            {
+                                const double x = ST(th, K_X0, cc);
+                                double csx = ST(th, K_CSX, cc);
+                                double s = th.q[6][cc] * (1. / 72.);
+                                s = fma(th.q[5][cc], 1. / 56., s); s = fma(th.q[4][cc], 1. / 42., s); s = fma(th.q[3][cc], 1. / 30., s);
+                                s = fma(th.q[2][cc], 1. / 20., s); s = fma(th.q[1][cc], 1. / 12., s); s = fma(th.q[0][cc], 1. / 6., s);
+                                s = fma(th.a0[cc], 0.5, s);
+                                csx += fma(s, dt2, th.v0[cc] * dt_done);
+                                const double xnew = x + csx;
+                                csx += x - xnew;
+                                ST(th, K_X0, cc) = xnew; ST(th, K_CSX, cc) = csx;
+                            }
+                            {
+                                const double v = th.v0[cc];
+                                double csv = ST(th, K_CSV, cc);
+                                double s = th.q[6][cc] * (1. / 8.);
+                                s = fma(th.q[5][cc], 1. / 7., s); s = fma(th.q[4][cc], 1. / 6., s); s = fma(th.q[3][cc], 1. / 5., s);
+                                s = fma(th.q[2][cc], 1. / 4., s); s = fma(th.q[1][cc], 1. / 3., s); s = fma(th.q[0][cc], 1. / 2., s);
+                                s += th.a0[cc];
+                                csv = fma(s, dt_done, csv);
+                                th.v0[cc] = v + csv;
+                                csv += v - th.v0[cc];
+                                ST(th, K_CSV, cc) = csv;
+                            }
+                            double _e[7], _b[7], e[7];
+#pragma unroll
+                            for (int k = 0; k < 7; k++) {
+                                _e[k] = ST(th, K_E + k, cc);
+                                _b[k] = th.q[k][cc];
+                                ST(th, K_ER + k, cc) = _e[k];
+                                ST(th, K_BR + k, cc) = _b[k];
+                            }
+                            var_predict<NC>(q, _e, _b, e, th.q, cc);
+#pragma unroll
+                            for (int k = 0; k < 7; k++) ST(th, K_E + k, cc) = e[k];
+                        }
+                    });
+                    w.t += dt_done;
+                    w.dt_last_done = dt_done;
+                    result = 1;
+                }
+                // publish x0 of the producer sets for the encounter test and the next attempt's a0
+                publish_positions(0, false);
+                ex.sync();
+                if (var_encounter<P, D>(cbuf, u)) result |= 2;
+                return result;
+            };
+
+            // ---- the reference's epoch loop (state.py:262-284): forward in order, backward reversed ----
+            for (int ii = 0; ii < n && final_status < 0; ii++) {
+                const int ie = backward ? (base + n - 1 - ii) : (base + ii);
+                c.tmax = a.ot[ie];
+                c.last_full_dt = w.dt;
+                w.dt_last_done = 0.0;
+                c.status = RUN;
+                if (var_encounter<P, D>(cbuf, u)) c.status = ST_ENCOUNTER;
+                while (check_exit(w, c) < 0) {
+                    int r;
+                    bool dead = false;
+                    for (;;) {
+                        r = attempt();
+                        c.attempts++;
+                        if (c.attempts > md->max_attempts || !isfinite(w.dt) || w.dt == 0.0) { dead = true; break; }
+                        if (r & 1) break;
+                    }
+                    if (dead) { c.status = ST_NONFINITE; break; }
+                    if (r & 2) c.status = ST_ENCOUNTER;
+                }
+                w.dt = c.last_full_dt;
+                if (c.status != ST_OK) { final_status = c.status; break; }
+                // epoch reached: star vx of every set, chi2 / d / dd sums (state.py:264-271)
+                ex.each([&](Var2Thread<P, D>& th) {
+                    if (th.role < 0) return;
+#pragma unroll
+                    for (int p = 0; p < P; p++) vxs[th.set * P + p] = th.v0[p * D];
+                });
+                ex.sync();
+                const double svx = var_star_vx<P>(vxs, dm, u, 0, 0, 0, 0, 0, 0);
+                if (!isfinite(svx)) {
+                    final_status = ST_NONFINITE;
+                } else {
+                    const double res = svx - a.orv[ie], er = a.oerr[ie];
+                    const double den = er * er * a.npoints;
+                    ex.each([&](Var2Thread<P, D>& th) {
+                        if (th.role < 0) return;
+                        if (th.role == 0) {
+                            th.acc += res * res / den;
+                        } else if (th.role == 1) {
+                            const double da = var_star_vx<P>(vxs, dm, u, 1, th.set, 0, 0, th.pa, 0);
+                            th.acc += 2. * da * res / den;
+                        } else {
+                            const double da = var_star_vx<P>(vxs, dm, u, 1, 1 + th.pa, 0, 0, th.pa, 0);
+                            const double db = var_star_vx<P>(vxs, dm, u, 1, 1 + th.pb, 0, 0, th.pb, 0);
+                            const double dab = var_star_vx<P>(vxs, dm, u, 2, th.set, 1 + th.pa, 1 + th.pb, th.pa, th.pb);
+                            th.acc += 2. * dab * res / den + 2. * da * db / den;
+                        }
+                    });
+                }
+                ex.sync();
+            }
+            if (final_status < 0) final_status = ST_OK;
+        }
+        const int fs = final_status;
+        ex.each([&](Var2Thread<P, D>& th) {
+            if (th.tid == 0) a.part_status[item] = fs;
+            if (fs == ST_OK && th.role >= 0) a.part[item * L.nsets + th.set] = th.acc;
+        });
+        ex.add_work(a.work_counters, n_force, n_attempt);
+    }
+}
+
+}  // namespace rv

@@ -6,6 +6,7 @@
 #include <string.h>
 #include <vector>
 #include "../../rvel_mcmc_b200/csrc/rv_var.cuh"
+#include "../../rvel_mcmc_b200/csrc/rv_var2.cuh"
 #include "../../rvel_mcmc_b200/csrc/rv_model.h"
 
 namespace {
@@ -33,7 +34,37 @@ int run(const rv::VarArgs& a, int nv) {
     rv::var_run_items<P, D>(ex, a, L, sm.data());
     return 0;
 }
+// the set-per-lane layout (rv_var2.cuh): barriers and named-barrier signals are no-ops in a sequential run because
+// every phase is completed for all threads before the next one starts
+template <int P, int D>
+struct HostVar2Exec {
+    std::vector<rv::Var2Thread<P, D>> th;
+    double cur[2] = {0.0, 0.0};
+    template <class F> void each(F&& f) { for (auto& t : th) f(t); }
+    void sync() {}
+    void producer_sync() {}
+    void signal(int) {}
+    void wait(int) {}
+    void stage_max(const rv::Var2Thread<P, D>&, double a, double b) { if (a > cur[0]) cur[0] = a; if (b > cur[1]) cur[1] = b; }
+    void read_max(double& a, double& b) { a = cur[0]; b = cur[1]; cur[0] = cur[1] = 0.0; }
+    long long fetch(unsigned long long* ctr) { return (long long)((*ctr)++); }
+    void add_work(unsigned long long* wc, unsigned long long nf, unsigned long long na) { if (wc) { wc[0] += nf; wc[1] += na; } }
+};
+
+template <int P, int D>
+int run2(const rv::VarArgs& a, int nv) {
+    const rv::Var2Layout L = rv::var2_layout(P, D, nv);
+    std::vector<double> sm((size_t)L.total, 0.0);
+    HostVar2Exec<P, D> ex;
+    ex.th.resize(L.NT);
+    for (int t = 0; t < L.NT; t++) rv::var2_assign(ex.th[t], t, L);
+    rv::var2_run_items<P, D>(ex, a, L, sm.data());
+    return 0;
+}
 }  // namespace
+
+static int g_var_layout = 0;      // 0: thread per (set, planet) (rv_var.cuh); 2: lane per set (rv_var2.cuh)
+extern "C" void mirror_set_var_layout(int v) { g_var_layout = v; }
 
 extern "C" int mirror_loglik_d_dd(int P, const double* fixed, int nvars, const int* fp, const int* fe, double hill, int dims,
                                   const double* tf, const double* rvf, const double* ef, int nf,
@@ -55,8 +86,12 @@ extern "C" int mirror_loglik_d_dd(int P, const double* fixed, int nvars, const i
     a.model = &m; a.theta = theta; a.W = W;
     a.ot = ot.data(); a.orv = orv.data(); a.oerr = oerr.data(); a.nf = nf; a.nb = nb; a.npoints = npoints; a.check_prior = m.check_prior;
     a.part = part.data(); a.part_status = pst.data(); a.item_counter = &ctr; a.work_counters = work;
-    const int key = P * 10 + m.D;
+    const int key = P * 10 + m.D + (g_var_layout == 2 ? 100 : 0);
     switch (key) {
+        case 112: run2<1, 2>(a, nvars); break;
+        case 113: run2<1, 3>(a, nvars); break;
+        case 122: run2<2, 2>(a, nvars); break;
+        case 123: run2<2, 3>(a, nvars); break;
         case 12: run<1, 2>(a, nvars); break;
         case 13: run<1, 3>(a, nvars); break;
         case 22: run<2, 2>(a, nvars); break;

@@ -18,6 +18,15 @@ def _hd():
     return T.load_vels("HD155358.vels")
 
 
+@pytest.fixture(params=[0, 2], ids=["thread-per-set-planet", "lane-per-set"])
+def var_layout(request):
+    """Both CTA algorithms run through the same emulation tests: rv_var.cuh (one thread per (set, planet); three-planet
+    systems) and rv_var2.cuh (one lane per set, producer warp; one- and two-planet systems)."""
+    T.mirror().mirror_set_var_layout(request.param)
+    yield request.param
+    T.mirror().mirror_set_var_layout(0)
+
+
 def _var_logp(obs, theta):
     """logp on the variational path's step sequence (forward + monotone backward), value only."""
     lo, _, _, so, _ = T.orc_logp_d_dd_batch(Z2, T.FP10, T.FE10, 2.0, obs, np.atleast_2d(theta))
@@ -68,7 +77,7 @@ def test_norm_choice_changes_derivatives_below_tolerance():
     assert b[4][1] > a[4][1]      # the 2017-era norm takes more steps
 
 
-def test_block_emulation_matches_oracle_hd155358():
+def test_block_emulation_matches_oracle_hd155358(var_layout):
     obs = _hd()
     theta = T.gaussian_ball(T.HD_SOL, T.HD_SCALE_VEC, 3, 5)
     theta[0] = T.HD_SOL
@@ -81,7 +90,7 @@ def test_block_emulation_matches_oracle_hd155358():
     assert (np.abs(hm - ho) / (np.abs(ho) + 1e-6 * np.abs(ho).max())).max() < 1e-7
 
 
-def test_block_emulation_prior_and_encounter_status():
+def test_block_emulation_prior_and_encounter_status(var_layout):
     obs = _hd()
     theta = np.array([T.HD_SOL, T.KAT5[1][0], T.HD_SOL])
     theta[2][3] = 1e-6                              # m <= 5e-6: hard prior
@@ -97,8 +106,15 @@ def test_block_emulation_prior_and_encounter_status():
     ([{"m": 1e-3, "a": 0.3, "h": 0.02, "k": -0.03, "l": 0.4, "ix": 0.1, "iy": -0.05}], [("a", "ix", "m", "l", "iy")]),
     ([{"m": 0.92e-3, "a": 0.2275, "h": -0.06, "k": 0.015, "l": -1.0}, {"m": 1.95e-3, "a": 0.3665, "h": 0.02, "k": 0.0, "l": 2.1},
       {"m": 1e-3, "a": 0.59, "h": 0.0, "k": 0.03, "l": 0.7}], [("a", "m"), ("h", "l"), ("a", "k", "m")]),
+    ([{"m": 0.92e-3, "a": 0.2275, "h": -0.06, "k": 0.015, "l": -1.0, "ix": 0.05, "iy": 0.02},
+      {"m": 1.95e-3, "a": 0.3665, "h": 0.02, "k": 0.0, "l": 2.1, "ix": -0.03, "iy": 0.0}],
+     [("a", "ix", "m", "l"), ("h", "k", "m", "iy")]),
+    ([{"m": 0.92e-3, "a": 0.2275, "h": -0.06, "k": 0.015, "l": -1.0}, {"m": 1.95e-3, "a": 0.3665, "h": 0.02, "k": 0.0, "l": 2.1}],
+     [("m",), ("m",)]),
 ])
-def test_block_emulation_other_shapes(planets, free):
+def test_block_emulation_other_shapes(planets, free, var_layout):
+    if var_layout == 2 and len(planets) > 2:
+        pytest.skip("the lane-per-set layout carries one or two planets")
     E = T.elems_from_planets(planets)
     fp, fe, th = [], [], []
     for i, keys in enumerate(free):
