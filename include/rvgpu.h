@@ -76,6 +76,8 @@ int rv_model_destroy(rv_model* model);
 /* options: "integrator" (0 = IAS15, rebound's default and what the reference runs; 1 = WHFast, fixed step "dt0", each leg
  *   swept monotonically -- no reference call site, parity unpinned; rv_loglik_d_dd / rv_smala_run refuse it),
  * "dt0" (1e-3), "epsilon" (1e-9), "max_attempts", "hill_factor", "mapping" (0 lane-per-planet, 1 thread-per-walker),
+ * "var_layout" (variational kernel: 0 = one lane per variational set where available (one or two planets), 1 = one
+ *   thread per (set, planet)),
  * "check_prior" (1; 0 = rv_loglik_d_dd / rv_loglik_d_dd_dev integrate even outside the hard prior, as state.py:290
  *   does; the samplers ignore it and always test the prior; prefer rv_loglik_d_dd_opt's per-call argument),
  * "monotone_backward" (0 = rv_loglik visits obs.tb in its stored order as state.py:91 does; 1 = one sweep from 0 to the
@@ -145,6 +147,17 @@ int rv_stretch_run(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, double
 int rv_stretch_half_dev(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, double* d_S, int64_t nS,
                         uint64_t id0_S, const double* d_C, int64_t nC, double* d_lnp_S, double a, uint64_t seed,
                         uint32_t step, uint32_t half, uint64_t* d_n_accept, uint8_t* d_accepted, void* stream);
+
+/* The same ensemble over several GPUs of ONE process (one rv_ctx / rv_model / rv_obs per GPU, same schema and data on each):
+ * every GPU keeps a full copy of the ensemble and owns one slice of each half; a slice's accept kernel stores its accepted
+ * walkers into every copy through peer-mapped pointers (NVLink P2P), events order the half-steps across devices -- there
+ * is no separate exchange step and no host synchronisation inside the loop.  W/2 must be a multiple of n_gpus; all pairs of
+ * GPUs need peer access (-40 otherwise).  Results are bit-identical to rv_stretch_run for every n_gpus (random numbers are
+ * keyed by the ensemble index).  Reference semantics: Ensemble.step, mcmc.py:57-65.                                   */
+int rv_stretch_run_multi(int n_gpus, rv_ctx* const* ctxs, const rv_model* const* models, const rv_obs* const* obss,
+                         double* theta, double* lnp, int have_lnp, double a, uint64_t seed, uint32_t first_step, int nsteps,
+                         int thin, int64_t W, double* chain, double* chain_lnp, uint64_t* n_accept);
+
 
 /* nsteps MH steps on DEVICE buffers (chains sharded over GPUs need no exchange). */
 int rv_mh_steps_dev(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, double* d_theta, double* d_logp,

@@ -30,7 +30,7 @@ def lib_path():
 
 
 _lib = None
-_lib_lock = threading.Lock()
+_lib_lock = threading.RLock()       # re-entrant: default_context() -> Context() -> load()
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
 
@@ -73,6 +73,9 @@ _SIGNATURES = {
     "rv_stretch_half_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_uint64, C.c_void_p,
                                       C.c_int64, C.c_void_p, C.c_double, C.c_uint64, C.c_uint32, C.c_uint32,
                                       C.c_void_p, C.c_void_p, C.c_void_p]),
+    "rv_stretch_run_multi": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                       C.c_double, C.c_uint64, C.c_uint32, C.c_int, C.c_int, C.c_int64, C.c_void_p,
+                                       C.c_void_p, C.c_void_p]),
     "rv_mh_steps_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
                                   C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]),
     "rv_dev_alloc": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_void_p)]),
@@ -448,6 +451,27 @@ class ModelHandle(_Handle):
                                                     int(first_step), int(nsteps), int(W),
                                                     C.c_void_p(d_n_accept) if d_n_accept else None,
                                                     C.c_void_p(stream) if stream else None), "rv_mh_steps_dev")
+
+def stretch_run_multi(models, obss, theta, nsteps, a=2.0, seed=0, first_step=0, thin=1, lnp=None, record_chain=True):
+    """Affine stretch ensemble over several GPUs of this process (rv_stretch_run_multi): models[g] / obss[g] are the
+    handles of GPU g (same schema and data on each).  Returns the dict of ModelHandle.stretch_run (without `accepted`);
+    bit-identical to the single-GPU run."""
+    G = len(models)
+    ctx0 = models[0].ctx
+    theta = models[0]._theta(theta).copy()
+    W = theta.shape[0]
+    have = lnp is not None
+    lp = _f64(lnp).copy() if have else np.zeros(W)
+    rows = nsteps // thin
+    chain = np.zeros((rows, W, models[0].nvars)) if record_chain else None
+    chain_lp = np.zeros((rows, W)) if record_chain else None
+    nacc = np.zeros(W, dtype=np.uint64)
+    arr = lambda hs: (C.c_void_p * G)(*[h.h for h in hs])
+    ctx0.check(ctx0.lib.rv_stretch_run_multi(G, arr([m.ctx for m in models]), arr(models), arr(obss), _ptr(theta), _ptr(lp),
+                                             1 if have else 0, float(a), int(seed), int(first_step), int(nsteps), int(thin), W,
+                                             _ptr(chain), _ptr(chain_lp), _ptr(nacc)), "rv_stretch_run_multi")
+    return dict(theta=theta, lnp=lp, chain=chain, chain_lnp=chain_lp, n_accept=nacc)
+
 
 _default_ctx = None
 

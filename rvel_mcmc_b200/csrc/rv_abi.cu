@@ -610,6 +610,170 @@ int rv_stretch_run(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, double
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// The stretch ensemble over several GPUs of ONE process (a context group driving several GPUs).
+// Every GPU holds the whole ensemble (theta[W][nv], lnp[W]); GPU g owns the g-th slice of each half.  Per half-step each GPU
+// proposes for its slice against the complementary half of ITS copy, integrates, and its accept kernel stores accepted walkers
+// into all copies over peer memory.  A half-step on GPU g may start once every GPU has finished the previous one (events).
+int rv_stretch_run_multi(int n_gpus, rv_ctx* const* ctxs, const rv_model* const* models, const rv_obs* const* obss,
+                         double* theta, double* lnp, int have_lnp, double a, uint64_t seed, uint32_t first_step, int nsteps,
+                         int thin, int64_t W, double* chain, double* chain_lnp, uint64_t* n_accept) {
+    rv_ctx* c0 = (n_gpus > 0 && ctxs) ? ctxs[0] : nullptr;
+    if (n_gpus < 1 || n_gpus > rv::RV_MAX_GROUP || !ctxs || !models || !obss || !theta || !lnp)
+        return fail(c0, -1, "rv_stretch_run_multi: bad argument (1..%d GPUs)", rv::RV_MAX_GROUP);
+    for (int g = 0; g < n_gpus; g++)
+        if (!ctxs[g] || !models[g] || !obss[g]) return fail(c0, -1, "rv_stretch_run_multi: NULL handle for GPU %d", g);
+    const int G = n_gpus;
+    if (W < 2 || (W & 1) || (W / 2) % G) return fail(c0, -2, "rv_stretch_run_multi: %lld walkers do not split into two halves of %d equal slices", (long long)W, G);
+    if (nsteps < 0) return fail(c0, -2, "rv_stretch_run_multi: negative nsteps");
+    if (thin < 1) thin = 1;
+    const int nv = models[0]->h.nvars;
+    for (int g = 1; g < G; g++)
+        if (models[g]->h.nvars != nv || models[g]->h.P != models[0]->h.P) return fail(c0, -2, "rv_stretch_run_multi: the models differ");
+    const size_t nvs = (size_t)(nv > 0 ? nv : 1);
+    const int64_t h = W / 2, n_loc = h / G;
+    const long long rows = chain ? nsteps / thin : 0;
+    rv::PeerCopies pc;
+    memset(&pc, 0, sizeof pc);
+    pc.n = G;
+    unsigned long long* d_nacc[rv::RV_MAX_GROUP] = {nullptr};
+    cudaEvent_t ev[rv::RV_MAX_GROUP][2];
+    memset(ev, 0, sizeof ev);
+    double *d_chain = nullptr, *d_chainlp = nullptr;
+    int rc = 0;
+    auto cleanup = [&]() {
+        for (int g = 0; g < G; g++) {
+            cudaSetDevice(ctxs[g]->device);
+            cudaStreamSynchronize(ctxs[g]->stream);
+            cudaFree(pc.theta[g]); cudaFree(pc.lnp[g]); cudaFree(d_nacc[g]);
+            for (int k = 0; k < 2; k++) if (ev[g][k]) cudaEventDestroy(ev[g][k]);
+        }
+        cudaSetDevice(ctxs[0]->device);
+        cudaFree(d_chain); cudaFree(d_chainlp);
+    };
+#define CUM(ctx, call)                                                                                 \
+    do {                                                                                               \
+        cudaError_t e__ = (call);                                                                      \
+        if (e__ != cudaSuccess) {                                                                      \
+            rc = fail(ctx, -100, "%s: %s", #call, cudaGetErrorString(e__));                            \
+            cleanup();                                                                                 \
+            return rc;                                                                                 \
+        }                                                                                              \
+    } while (0)
+    // peer access, buffers, events
+    for (int g = 0; g < G; g++) {
+        rv_ctx* c = ctxs[g];
+        CUM(c, cudaSetDevice(c->device));
+        for (int q = 0; q < G; q++) {
+            if (q == g || ctxs[q]->device == c->device) continue;
+            int can = 0;
+            CUM(c, cudaDeviceCanAccessPeer(&can, c->device, ctxs[q]->device));
+            if (!can) { rc = fail(c0, -40, "rv_stretch_run_multi: GPU %d cannot map GPU %d's memory (no peer access)", c->device, ctxs[q]->device); cleanup(); return rc; }
+            cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[q]->device, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+            else if (e != cudaSuccess) { rc = fail(c0, -100, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e)); cleanup(); return rc; }
+        }
+        CUM(c, cudaMalloc((void**)&pc.theta[g], (size_t)W * nvs * sizeof(double)));
+        CUM(c, cudaMalloc((void**)&pc.lnp[g], (size_t)W * sizeof(double)));
+        CUM(c, cudaMalloc((void**)&d_nacc[g], (size_t)2 * n_loc * sizeof(unsigned long long)));
+        CUM(c, cudaEventCreateWithFlags(&ev[g][0], cudaEventDisableTiming));
+        CUM(c, cudaEventCreateWithFlags(&ev[g][1], cudaEventDisableTiming));
+        CUM(c, cudaMemcpyAsync(pc.theta[g], theta, (size_t)W * nv * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        CUM(c, cudaMemsetAsync(d_nacc[g], 0, (size_t)2 * n_loc * sizeof(unsigned long long), c->stream));
+        if (int r2 = ensure(c, &c->d_prop, &c->cap_prop, (size_t)n_loc * nvs)) { cleanup(); return r2; }
+        if (int r2 = ensure(c, &c->d_plogp, &c->cap_plogp, (size_t)n_loc)) { cleanup(); return r2; }
+        if (int r2 = ensure(c, &c->d_pstatus, &c->cap_pstatus, (size_t)W)) { cleanup(); return r2; }
+        if (int r2 = ensure(c, &c->d_zz, &c->cap_zz, (size_t)n_loc)) { cleanup(); return r2; }
+    }
+    if (rows) {
+        CUM(c0, cudaSetDevice(c0->device));
+        CUM(c0, cudaMalloc((void**)&d_chain, (size_t)rows * W * nvs * sizeof(double)));
+        CUM(c0, cudaMalloc((void**)&d_chainlp, (size_t)rows * W * sizeof(double)));
+    }
+    // lnprob0: every GPU evaluates the whole ensemble copy it holds?  No -- its own two slices, then the slices are exchanged
+    // by plain peer copies (once); with have_lnp the caller's values are uploaded to every copy.
+    for (int g = 0; g < G; g++) {
+        rv_ctx* c = ctxs[g];
+        CUM(c, cudaSetDevice(c->device));
+        if (have_lnp) {
+            CUM(c, cudaMemcpyAsync(pc.lnp[g], lnp, (size_t)W * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        } else {
+            for (int half = 0; half < 2; half++) {
+                const int64_t lo = half * h + g * n_loc;
+                if (int r2 = loglik_dev_impl(c, models[g], obss[g], pc.theta[g] + (size_t)lo * nv, n_loc, pc.lnp[g] + lo,
+                                             c->d_pstatus + lo, c->stream)) { cleanup(); return r2; }
+                CUM(c, rv::launch_mask_logp(pc.lnp[g] + lo, c->d_pstatus + lo, n_loc, c->stream));
+            }
+        }
+    }
+    if (!have_lnp) {
+        for (int g = 0; g < G; g++) { CUM(ctxs[g], cudaSetDevice(ctxs[g]->device)); CUM(ctxs[g], cudaStreamSynchronize(ctxs[g]->stream)); }
+        for (int g = 0; g < G; g++)
+            for (int q = 0; q < G; q++) {
+                if (q == g) continue;
+                for (int half = 0; half < 2; half++) {
+                    const int64_t lo = half * h + g * n_loc;
+                    CUM(ctxs[g], cudaMemcpyPeerAsync(pc.lnp[q] + lo, ctxs[q]->device, pc.lnp[g] + lo, ctxs[g]->device,
+                                                     (size_t)n_loc * sizeof(double), ctxs[g]->stream));
+                }
+            }
+    }
+    for (int g = 0; g < G; g++) { CUM(ctxs[g], cudaSetDevice(ctxs[g]->device)); CUM(ctxs[g], cudaStreamSynchronize(ctxs[g]->stream)); }
+    // the sampling loop: asynchronous on G streams, ordered across devices by events
+    long long row = 0;
+    int phase = 0;
+    bool have_prev = false;
+    for (int k = 0; k < nsteps; k++) {
+        const unsigned step = first_step + (unsigned)k;
+        for (unsigned half = 0; half < 2; half++, phase ^= 1) {
+            for (int g = 0; g < G; g++) {
+                rv_ctx* c = ctxs[g];
+                CUM(c, cudaSetDevice(c->device));
+                if (have_prev)
+                    for (int q = 0; q < G; q++)
+                        if (q != g) CUM(c, cudaStreamWaitEvent(c->stream, ev[q][phase ^ 1], 0));
+                const int64_t lo = (int64_t)half * h + g * n_loc;
+                const double* C = pc.theta[g] + (half == 0 ? (size_t)h * nv : 0);
+                CUM(c, rv::launch_stretch_propose(pc.theta[g] + (size_t)lo * nv, C, nv, n_loc, h, a, seed, (uint64_t)lo, step, half,
+                                                  c->d_prop, c->d_zz, c->stream));
+                if (int r2 = loglik_dev_impl(c, models[g], obss[g], c->d_prop, n_loc, c->d_plogp, c->d_pstatus, c->stream)) { cleanup(); return r2; }
+                CUM(c, rv::launch_stretch_accept_peer(pc, g, lo, c->d_prop, c->d_plogp, c->d_pstatus, c->d_zz, nv, n_loc, seed,
+                                                      (uint64_t)lo, step, half, d_nacc[g] + half * n_loc, c->stream));
+                CUM(c, cudaEventRecord(ev[g][phase], c->stream));
+            }
+            have_prev = true;
+        }
+        if (rows && ((k + 1) % thin == 0)) {
+            // GPU 0's copy is complete once every GPU has finished this step's second half-step
+            CUM(c0, cudaSetDevice(c0->device));
+            for (int q = 1; q < G; q++) CUM(c0, cudaStreamWaitEvent(c0->stream, ev[q][phase ^ 1], 0));
+            CUM(c0, cudaMemcpyAsync(d_chain + (size_t)row * W * nv, pc.theta[0], (size_t)W * nv * sizeof(double), cudaMemcpyDeviceToDevice, c0->stream));
+            CUM(c0, cudaMemcpyAsync(d_chainlp + (size_t)row * W, pc.lnp[0], (size_t)W * sizeof(double), cudaMemcpyDeviceToDevice, c0->stream));
+            // the other GPUs must not overwrite GPU 0's copy before the snapshot is taken: they wait on this event next
+            CUM(c0, cudaEventRecord(ev[0][phase ^ 1], c0->stream));
+            row++;
+        }
+    }
+    for (int g = 0; g < G; g++) { CUM(ctxs[g], cudaSetDevice(ctxs[g]->device)); CUM(ctxs[g], cudaStreamSynchronize(ctxs[g]->stream)); }
+    CUM(c0, cudaSetDevice(c0->device));
+    CUM(c0, cudaMemcpyAsync(theta, pc.theta[0], (size_t)W * nv * sizeof(double), cudaMemcpyDeviceToHost, c0->stream));
+    CUM(c0, cudaMemcpyAsync(lnp, pc.lnp[0], (size_t)W * sizeof(double), cudaMemcpyDeviceToHost, c0->stream));
+    if (rows) {
+        CUM(c0, cudaMemcpyAsync(chain, d_chain, (size_t)rows * W * nv * sizeof(double), cudaMemcpyDeviceToHost, c0->stream));
+        if (chain_lnp) CUM(c0, cudaMemcpyAsync(chain_lnp, d_chainlp, (size_t)rows * W * sizeof(double), cudaMemcpyDeviceToHost, c0->stream));
+    }
+    CUM(c0, cudaStreamSynchronize(c0->stream));
+    if (n_accept)
+        for (int g = 0; g < G; g++) {
+            CUM(ctxs[g], cudaSetDevice(ctxs[g]->device));
+            for (int half = 0; half < 2; half++)
+                CUM(ctxs[g], cudaMemcpy(n_accept + half * h + g * n_loc, d_nacc[g] + half * n_loc, (size_t)n_loc * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+        }
+    cleanup();
+#undef CUM
+    return 0;
+}
+
 // SMALA (bern_a < 0) and ALSMALA (bern_a >= 0: step i is a full SMALA step with probability exp(-bern_a*i/niter_total),
 // driver.py:181, else a MALA step on the stale derivatives) share one implementation.
 static int smala_impl(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, double* theta, double* logp, double eps,

@@ -44,5 +44,12 @@ cudaError_t launch_smala_accept(double* theta, double* logp, double* grad, doubl
                                 unsigned long long seed, unsigned long long first_id, unsigned step,
                                 unsigned long long* n_accept, unsigned char* accepted, int* flag, double* chain_row,
                                 double* chain_logp_row, double* scratch, int mala, cudaStream_t s);
+// multi-GPU stretch: the full ensemble copies of every GPU of a group (own + peer-mapped pointers)
+constexpr int RV_MAX_GROUP = 16;
+struct PeerCopies { double* theta[RV_MAX_GROUP]; double* lnp[RV_MAX_GROUP]; int n; };
+cudaError_t launch_stretch_accept_peer(const PeerCopies& pc, int self, long long row0, const double* q, const double* q_lnp,
+                                       const int* q_status, const double* zz, int nvars, long long nS, unsigned long long seed,
+                                       unsigned long long id0_S, unsigned step, unsigned half, unsigned long long* n_accept,
+                                       cudaStream_t s);
 cudaError_t launch_mask_logp(double* logp, const int* status, long long W, cudaStream_t s);
 }  // namespace rv

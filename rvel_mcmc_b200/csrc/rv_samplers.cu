@@ -100,6 +100,33 @@ __global__ void stretch_accept_kernel(double* __restrict__ S, double* __restrict
     if (accepted) accepted[i] = acc ? 1 : 0;
 }
 
+// Multi-GPU stretch move: accept + exchange in one kernel.  Every GPU of the group holds a full copy of the ensemble
+// (positions and lnp); the GPU that owns a slice decides its accepts and writes each accepted walker straight into every
+// copy -- its own and, through peer-mapped pointers (NVLink P2P stores), the other GPUs' -- so there is no separate
+// all-gather step; cross-device ordering is by events on the streams (rv_stretch_run_multi).
+__global__ void stretch_accept_peer_kernel(PeerCopies pc, int self, long long row0, const double* __restrict__ q,
+                                           const double* __restrict__ q_lnp, const int* __restrict__ q_status,
+                                           const double* __restrict__ zz, int nvars, long long nS, unsigned long long seed,
+                                           unsigned long long id0_S, unsigned step, unsigned half,
+                                           unsigned long long* __restrict__ n_accept) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nS) return;
+    const unsigned long long id = id0_S + (unsigned long long)i;
+    const U4 r = philox4x32_10(seed, id, step, RNG_STRETCH_Z + half);
+    const double u = u53(r.z, r.w);
+    const double newlnp = (q_status[i] == ST_OK) ? q_lnp[i] : -INFINITY;
+    const long long row = row0 + i;
+    const double lnpdiff = (double)(nvars - 1) * log(zz[i]) + newlnp - pc.lnp[self][row];
+    if (lnpdiff > log(u)) {
+        for (int g = 0; g < pc.n; g++) {
+            double* __restrict__ dst = pc.theta[g] + row * nvars;
+            for (int v = 0; v < nvars; v++) dst[v] = q[i * nvars + v];
+            pc.lnp[g][row] = newlnp;
+        }
+        if (n_accept) n_accept[i] += 1ull;
+    }
+}
+
 __global__ void mask_logp_kernel(double* __restrict__ logp, const int* __restrict__ status, long long W) {
     const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (w < W && status[w] != ST_OK) logp[w] = -INFINITY;
@@ -133,6 +160,14 @@ cudaError_t launch_stretch_accept(double* S, double* lnp, const double* q, const
                                   unsigned char* accepted, cudaStream_t s) {
     stretch_accept_kernel<<<nblk(nS, 128), 128, 0, s>>>(S, lnp, q, q_lnp, q_status, zz, nvars, nS, seed, id0_S, step,
                                                         half, n_accept, accepted);
+    return cudaGetLastError();
+}
+cudaError_t launch_stretch_accept_peer(const PeerCopies& pc, int self, long long row0, const double* q, const double* q_lnp,
+                                       const int* q_status, const double* zz, int nvars, long long nS, unsigned long long seed,
+                                       unsigned long long id0_S, unsigned step, unsigned half, unsigned long long* n_accept,
+                                       cudaStream_t s) {
+    stretch_accept_peer_kernel<<<nblk(nS, 128), 128, 0, s>>>(pc, self, row0, q, q_lnp, q_status, zz, nvars, nS, seed, id0_S, step,
+                                                             half, n_accept);
     return cudaGetLastError();
 }
 cudaError_t launch_mask_logp(double* logp, const int* status, long long W, cudaStream_t s) {

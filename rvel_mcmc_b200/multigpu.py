@@ -3,9 +3,9 @@ jobs).  A DeviceGroup owns one rv_ctx per visible GPU and shards a batch of para
 them by contiguous blocks, one host thread per GPU (ctypes releases the GIL during the library call).  Nothing crosses
 GPUs: MH / SMALA chains and likelihood batches are independent, and the random streams are keyed by the GLOBAL chain id,
 so the results are bit-identical to a single-GPU run.  The affine stretch ensemble needs one exchange per half-step:
-DeviceGroup.stretch_run keeps a full copy of the positions on every GPU and copies each GPU's freshly updated slice to
-the others with cudaMemcpyPeer (NVLink peer-to-peer DMA); under torchrun, samplers.stretch_run_sharded does the same with
-an NCCL all-gather."""
+DeviceGroup.stretch_run is one call into rv_stretch_run_multi: a full copy of the ensemble on every GPU, accepted walkers
+stored into all copies by the accept kernel itself over peer-mapped memory (NVLink P2P), half-steps ordered by events;
+under torchrun (one process per GPU), samplers.stretch_run_sharded does the exchange with an NCCL all-gather."""
 from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
@@ -97,71 +97,16 @@ class DeviceGroup(object):
             hs[r][1], theta[lo:hi], eps, alpha, nsteps, seed=seed, first_chain_id=first_chain_id + lo, **kw)))
 
 
-def _stretch_run(group, state, obs, theta0, nsteps, a=2.0, seed=0):
-    theta0 = np.ascontiguousarray(theta0, dtype=np.float64)
-    W, nv = theta0.shape
-    G = len(group.ctxs)
-    if W % 2 or (W // 2) % G:
-        raise ValueError("walkers (%d) must split evenly into two halves of %d-GPU slices" % (W, G))
-    h, n_loc = W // 2, (W // 2) // G
+def _stretch_run(group, state, obs, theta0, nsteps, a=2.0, seed=0, first_step=0, thin=1, lnp=None, record_chain=False):
+    """One library call (rv_stretch_run_multi): every GPU keeps a full copy of the ensemble, a slice's accept kernel stores
+    its accepted walkers into all copies over peer memory, events order the half-steps -- no host synchronisation and no
+    separate exchange inside the loop."""
     hs = group._handles(state, obs)
-    row = nv * 8
-    d_theta = [c.dev_alloc(W * row) for c in group.ctxs]
-    d_lnp = [c.dev_alloc(2 * n_loc * 8) for c in group.ctxs]
-    d_st = [c.dev_alloc(2 * n_loc * 4) for c in group.ctxs]
-    d_nacc = [c.dev_alloc(2 * n_loc * 8) for c in group.ctxs]
-    try:
-        def owned(r, half):
-            lo = half * h + r * n_loc
-            return lo, lo + n_loc
-
-        def init(r):
-            c, (m, oh) = group.ctxs[r], hs[r]
-            c.dev_upload(d_theta[r], theta0)
-            c.dev_upload(d_nacc[r], np.zeros(2 * n_loc, dtype=np.uint64))
-            for half in (0, 1):
-                lo, _ = owned(r, half)
-                m.loglik_dev(oh, d_theta[r] + lo * row, n_loc, d_lnp[r] + half * n_loc * 8, d_st[r] + half * n_loc * 4)
-            c.sync()
-            lnp = np.zeros(2 * n_loc); st = np.zeros(2 * n_loc, dtype=np.int32)
-            c.dev_download(lnp, d_lnp[r]); c.dev_download(st, d_st[r])
-            lnp[st != 0] = -np.inf                       # lnprob(): -inf on any failure (mcmc.py:28-35)
-            c.dev_upload(d_lnp[r], lnp)
-        list(group.pool.map(init, range(G)))
-        for k in range(nsteps):
-            for half in (0, 1):
-                def move(r):
-                    c, (m, oh) = group.ctxs[r], hs[r]
-                    lo, _ = owned(r, half)
-                    comp = d_theta[r] + (h if half == 0 else 0) * row
-                    m.stretch_half_dev(oh, d_theta[r] + lo * row, n_loc, lo, comp, h, d_lnp[r] + half * n_loc * 8, a, seed, k, half,
-                                       d_n_accept=d_nacc[r] + half * n_loc * 8)
-                    c.sync()
-                list(group.pool.map(move, range(G)))
-
-                def spread(r):                            # this GPU's updated slice -> every other GPU's copy
-                    lo, _ = owned(r, half)
-                    for q in range(G):
-                        if q != r:
-                            group.ctxs[r].dev_copy_to(group.ctxs[q], d_theta[q] + lo * row, d_theta[r] + lo * row, n_loc * row)
-                list(group.pool.map(spread, range(G)))
-        theta = np.zeros((W, nv)); group.ctxs[0].dev_download(theta, d_theta[0])
-        lnp = np.zeros(W); nacc = np.zeros(W, dtype=np.uint64)
-        for r in range(G):
-            part = np.zeros(2 * n_loc); pa = np.zeros(2 * n_loc, dtype=np.uint64)
-            group.ctxs[r].dev_download(part, d_lnp[r]); group.ctxs[r].dev_download(pa, d_nacc[r])
-            for half in (0, 1):
-                lo, hi = owned(r, half)
-                lnp[lo:hi] = part[half * n_loc:(half + 1) * n_loc]
-                nacc[lo:hi] = pa[half * n_loc:(half + 1) * n_loc]
-        return dict(theta=theta, lnp=lnp, n_accept=nacc)
-    finally:
-        for r, c in enumerate(group.ctxs):
-            for p in (d_theta[r], d_lnp[r], d_st[r], d_nacc[r]):
-                c.dev_free(p)
+    return _abi.stretch_run_multi([m for m, _ in hs], [o for _, o in hs], theta0, nsteps, a=a, seed=seed, first_step=first_step,
+                                  thin=thin, lnp=lnp, record_chain=record_chain)
 
 
-DeviceGroup.stretch_run = lambda self, state, obs, theta0, nsteps, a=2.0, seed=0: _stretch_run(self, state, obs, theta0, nsteps, a, seed)
+DeviceGroup.stretch_run = _stretch_run
 
 
 def _obs_handle(obs, ctx):

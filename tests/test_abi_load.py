@@ -43,3 +43,17 @@ def test_product_does_not_link_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "librvoracle" not in txt and "hostmirror" not in txt and "rv_oracle" not in txt, f
+
+
+def test_default_context_fails_loudly_without_a_gpu_and_does_not_deadlock():
+    """default_context() takes the module lock and then constructs a Context, which loads the library under the same lock."""
+    import subprocess
+    import sys
+    import rvtest as T
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "from rvel_mcmc_b200 import _abi\n"
+            "try:\n    _abi.default_context(); print('CTX')\n"
+            "except _abi.RvGpuError as e:\n    print('RvGpuError')\n") % T.ROOT
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert r.stdout.strip() in ("RvGpuError", "CTX")          # CTX on a GPU box, RvGpuError here; never a hang
