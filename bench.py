@@ -127,7 +127,7 @@ def oracle_batch(obs, theta, nthreads):
 # ---------------------------------------------------------------------------------------------------------------
 # ESS/s (BASELINE metric, second half): the three device samplers from an equilibrated start
 
-def run_ess(ctx, model, oh, rank, world, dist, dev, rows, torch):
+def run_ess(ctx, model, oh, rank, world, dist, dev, rows, torch, budgets=(80.0, 50.0, 90.0)):
     from rvel_mcmc_b200.samplers import ess
     from rvel_mcmc_b200 import driver
     if not os.path.exists(EQUILIBRATED):
@@ -138,7 +138,7 @@ def run_ess(ctx, model, oh, rank, world, dist, dev, rows, torch):
     out = {"start": "committed equilibrated stretch ensemble (%d walkers; tools/make_equilibrated_ensemble.py), no burn-in "
                     "inside the clock" % len(eq),
            "definition": "ESS = recorded rows x walkers / max_i tau_i; tau_int = Sokal's windowed integrated autocorrelation "
-                         "time (mean over 64 walkers per parameter), ac_time_ref = driver.py:366-377 (first lag with "
+                         "time of the walker-averaged autocovariance (256 walkers), ac_time_ref = driver.py:366-377 (first lag with "
                          "autocorrelation < 0.5; mean over 16 walkers, as driver.py:355-370 does for ensembles); seconds = "
                          "wall time of the whole library call (chain download included)",
            "aggregate": "sum over ranks of ESS / max over ranks of seconds; every rank runs its own chains (MH, SMALA: "
@@ -162,26 +162,43 @@ def run_ess(ctx, model, oh, rank, world, dist, dev, rows, torch):
         d.update(extra)
         out[name] = d
 
+    def sized(name, budget_s, pilot):
+        """Recorded rows for one sampler: `rows` unless the time budget says fewer (pilot = seconds of a 10-step run)."""
+        per_step = pilot / 10.0
+        n = int(min(rows, max(200, budget_s / max(per_step, 1e-6))))
+        out.setdefault("time_budget", {})[name] = {"budget_s": budget_s, "pilot_ms_per_step": 1e3 * per_step, "rows": n,
+                                                   "rows_limited_by_time_budget": bool(n < rows)}
+        return n
+
     # affine stretch: one full wave of (walker, leg) items per half-step
     W = min(len(eq), slots) & ~1
     t0 = time.perf_counter()
-    r = model.stretch_run(oh, eq[:W], rows, seed=11 + 1000 * rank, thin=1)
-    summarise("stretch", r["chain"], time.perf_counter() - t0, W * (rows + 1),
-              {"accept_rate": float(r["n_accept"].mean() / rows), "a": 2.0})
+    model.stretch_run(oh, eq[:W], 10, seed=1, record_chain=False)
+    n = sized("stretch", budgets[0], time.perf_counter() - t0)
+    t0 = time.perf_counter()
+    r = model.stretch_run(oh, eq[:W], n, seed=11 + 1000 * rank, thin=1)
+    summarise("stretch", r["chain"], time.perf_counter() - t0, W * (n + 1),
+              {"accept_rate": float(r["n_accept"].mean() / n), "a": 2.0})
     del r
     # Metropolis-Hastings: proposal scale 0.25 x the posterior standard deviations of the equilibrated ensemble
     W = min(len(eq), slots // 2)
     t0 = time.perf_counter()
-    r = model.mh_run(oh, eq[:W], post_std, 0.25, rows, seed=12, first_chain_id=rank * W, thin=1)
-    summarise("mh", r["chain"], time.perf_counter() - t0, W * (rows + 1),
-              {"accept_rate": float(r["n_accept"].mean() / rows), "step_size": 0.25, "scales": "posterior std"})
+    model.mh_run(oh, eq[:W], post_std, 0.25, 10, seed=1, record_chain=False)
+    n = sized("mh", budgets[1], time.perf_counter() - t0)
+    t0 = time.perf_counter()
+    r = model.mh_run(oh, eq[:W], post_std, 0.25, n, seed=12, first_chain_id=rank * W, thin=1)
+    summarise("mh", r["chain"], time.perf_counter() - t0, W * (n + 1),
+              {"accept_rate": float(r["n_accept"].mean() / n), "step_size": 0.25, "scales": "posterior std"})
     del r
-    # SMALA with the reference's step size and SoftAbs constant ((Ex)HD155358.ipynb:640): one wave of var_kernel CTAs
+    # SMALA with the reference's step size and SoftAbs constant ((Ex)HD155358.ipynb:640): one wave of variational CTAs
     W = ctx.device_info()["sm_count"] * 3 // 2
     t0 = time.perf_counter()
-    r = model.smala_run(oh, eq[:W], 0.025, 1.4, rows, seed=13, first_chain_id=rank * W, thin=1)
-    summarise("smala", r["chain"], time.perf_counter() - t0, W * (rows + 1),
-              {"accept_rate": float(r["n_accept"].mean() / rows), "eps": 0.025, "alpha": 1.4,
+    model.smala_run(oh, eq[:W], 0.025, 1.4, 10, seed=1, record_chain=False)
+    n = sized("smala", budgets[2], time.perf_counter() - t0)
+    t0 = time.perf_counter()
+    r = model.smala_run(oh, eq[:W], 0.025, 1.4, n, seed=13, first_chain_id=rank * W, thin=1)
+    summarise("smala", r["chain"], time.perf_counter() - t0, W * (n + 1),
+              {"accept_rate": float(r["n_accept"].mean() / n), "eps": 0.025, "alpha": 1.4,
                "not_spd_flags": int((r["status"] == 9).sum())})
     return out
 
@@ -337,7 +354,9 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0, help="walkers in the timed CPU sample (0: about 15 s of work)")
     ap.add_argument("--no-ess", action="store_true", help="skip the ESS/s block (three sampler runs, ~2 min)")
     ap.add_argument("--ess", action="store_true", help="(default on; kept for compatibility)")
-    ap.add_argument("--ess-rows", type=int, default=2000, help="recorded rows (= sampler steps) per ESS run")
+    ap.add_argument("--ess-rows", type=int, default=2000, help="recorded rows (= sampler steps) per ESS run (fewer if the "
+                                                               "per-sampler time budget says so; the line reports it)")
+    ap.add_argument("--ess-budget", default="80,50,90", help="seconds for the stretch, MH and SMALA ESS runs")
     ap.add_argument("--no-var", action="store_true")
     ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the sharded stretch block")
     ap.add_argument("--sharded-steps", type=int, default=6)
@@ -452,7 +471,8 @@ def main():
         sharded = run_stretch_sharded(ctx, model, oh, rank, world, dist, dev, torch, args.sharded_steps)
     ess_block = None
     if not args.no_ess:
-        ess_block = run_ess(ctx, model, oh, rank, world, dist if world > 1 else None, dev, args.ess_rows, torch)
+        ess_block = run_ess(ctx, model, oh, rank, world, dist if world > 1 else None, dev, args.ess_rows, torch,
+                            tuple(float(x) for x in args.ess_budget.split(",")))
     if rank != 0:
         if world > 1:
             dist.barrier()

@@ -120,6 +120,16 @@ static cudaError_t launch_loglik_var(const LoglikArgs& a, int P, int D, int mapp
 }
 
 cudaError_t launch_loglik(const LoglikArgs& a, int P, int D, int mapping, int dense, int num_sms, cudaStream_t stream) {
+    // tuning variants of the headline instantiation (tools/bench_variants.py): model option "mapping" >= 10
+    if (P == 2 && D == 2 && mapping >= 10 && !dense) {
+        switch (mapping) {
+            case 10: return launch_one<2, 2, 1, 128, 3, 2>(a, num_sms, stream);     // IAS15 tables from the constant bank
+            case 11: return launch_one<2, 2, 1, 128, 4, 0>(a, num_sms, stream);     // 4 CTAs per SM (<= 128 registers)
+            case 12: return launch_one<2, 2, 1, 128, 4, 2>(a, num_sms, stream);
+            case 13: return launch_one<2, 2, 1, 256, 2, 0>(a, num_sms, stream);     // 2 CTAs x 256 threads (<= 128 registers)
+            default: return cudaErrorInvalidValue;
+        }
+    }
     if (dense && !a.times) return launch_loglik_var<4>(a, P, D, mapping, num_sms, stream);
     return launch_loglik_var<0>(a, P, D, mapping, num_sms, stream);
 }

@@ -147,7 +147,8 @@ RV_HD int smala_accept_one(int n, const double* __restrict__ th, double logp, co
                            const double* __restrict__ p_grad, const double* __restrict__ p_hess, int p_status,
                            int geo_status, double q_fwd, double eps, double alpha, uint64_t seed, uint64_t id,
                            uint32_t step, int* flag, double* __restrict__ A) {
-    if (geo_status != ST_OK) { if (flag) *flag = ST_NOT_SPD; return 0; }
+    // a chain whose START state already carries a status (hard prior, Encounter) keeps that status: it can never move
+    if (geo_status != ST_OK) { if (flag && *flag == ST_OK) *flag = ST_NOT_SPD; return 0; }
     if (p_status != ST_OK) return 0;
     double *Q = A + n * n, *G = Q + n * n, *Gi = G + n * n;
     double logdetG;

@@ -20,8 +20,16 @@ def _utcnow():
 
 
 class Mcmc(object):
-    def __init__(self, initial_state, obs):
+    def __init__(self, initial_state, obs, fast=False):
+        """fast (not in the reference, mcmc.py:12-15): evaluate the plain likelihood with the dense-output option -- one
+        continuous IAS15 integration per leg with natural steps, velocities at the epochs read from the step's own
+        polynomial instead of rebound's truncated step per epoch.  Same logp to ~1e-12 (measured 1e-12 on the HD155358
+        ball, profiles/), a step count that no longer grows with the number of epochs, and ~3x lower latency per
+        evaluation -- which is what bounds a single chain / a small ensemble on the GPU.  The default (False) keeps the
+        reference's step sequence decision by decision."""
         self.state = initial_state.deepcopy()
+        if fast:
+            self.state.dense_output = True
         self.obs = obs
 
     def step(self):
@@ -139,8 +147,8 @@ class Ensemble(Mcmc):
     theta + 1e-3*scales*N(0,1) (numpy's global RNG, one normal(size=Nvars) per walker), and each step() is one
     stretch-move sweep over both half-ensembles, every half evaluated as ONE batched kernel call."""
 
-    def __init__(self, initial_state, obs, scales, nwalkers=10, live_dangerously=False):
-        Mcmc.__init__(self, initial_state, obs)
+    def __init__(self, initial_state, obs, scales, nwalkers=10, live_dangerously=False, fast=False):
+        Mcmc.__init__(self, initial_state, obs, fast=fast)
         self.set_scales(scales)
         self.nwalkers = nwalkers
         centre = self.state.get_params()
@@ -167,8 +175,8 @@ class Mh(Mcmc):
     reference: normal(size=Nvars) for the proposal, then -- only when the proposal passes the hard prior and
     integrates without an encounter -- one uniform() for the accept test."""
 
-    def __init__(self, initial_state, obs):
-        Mcmc.__init__(self, initial_state, obs)
+    def __init__(self, initial_state, obs, fast=False):
+        Mcmc.__init__(self, initial_state, obs, fast=fast)
         self.step_size = 3e-5
         self.scales = np.ones(self.state.Nvars)
 

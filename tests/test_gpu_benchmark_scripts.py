@@ -28,14 +28,20 @@ def _floats(line):
     return [float(x) for x in re.findall(r"[-+]?\d+\.?\d*(?:[eE][-+]?\d+)?", line.split(":", 1)[1])]
 
 
+def _vector_after(out, label):
+    """numpy prints a 10-vector over several lines: collect everything between `label` and the closing bracket."""
+    tail = out[out.index(label) + len(label):]
+    return _floats("x:" + tail[:tail.index("]")])
+
+
 @pytest.mark.parametrize("which,niter,nvars,fused", [
     ("mh", 300, 10, True), ("smala", 60, 10, True), ("emcee", 32 * 40, 10, True),
     ("smala", 12, 10, False), ("emcee", 32 * 6, 10, False),
 ])
 def test_benchmark_script_workloads_run_on_gpu(which, niter, nvars, fused):
     out = _run([SCRIPT, which, "--niter", str(niter)] + (["--fused"] if fused else []))
-    mean = _floats([l for l in out.splitlines() if l.startswith("mean:")][0])
-    true = _floats([l for l in out.splitlines() if l.startswith("true:")][0])
+    mean = _vector_after(out, "mean:")
+    true = _vector_after(out, "true:")
     assert len(mean) == nvars and len(true) == nvars and np.all(np.isfinite(mean))
     # short chains started at the truth stay near it (every parameter within 20 % of its scale or 0.2 absolute)
     assert np.all(np.abs(np.array(mean) - np.array(true)) < 0.2 * np.maximum(np.abs(true), 1.0))

@@ -32,7 +32,7 @@ for mp in [int(x) for x in sys.argv[1:]] or [0]:
         torch.cuda.synchronize(); best = min(best, e0.elapsed_time(e1))
     lp = logp.cpu().numpy()
     if ref is None: ref = lp.copy()
-    print("mapping %2d: %.2f ms  %.3f Mevals/s  max|dlogp vs first|=%.2e" % (mp, best, W / best / 1e3, np.abs(lp - ref).max()))
+    print("mapping %2d: %.2f ms  %.3f Mevals/s  max|dlogp vs first|=%.2e" % (mp, best, W / best / 1e3, np.abs(lp - ref).max()), flush=True)
 
 # non-default epoch handling: monotone backward sweep, dense output
 for key in ("monotone_backward", "dense_output"):

@@ -8,7 +8,7 @@ driver.py:416-425) must be below 0.03 for every parameter, while the first quart
 differ.  The final positions are the fixture.  Chains started in the ball need ~2000 ensemble steps to reach the posterior's
 spread (profiles/r01q_*), which is why bench.py does not burn in inside its clock.
 
-  python tools/make_equilibrated_ensemble.py [walkers=28416] [steps=6000]      (one B200, a few minutes)
+  python tools/make_equilibrated_ensemble.py [walkers=28416] [steps=4000]      (one B200, a few minutes)
 """
 import json
 import os
@@ -23,7 +23,7 @@ import rvtest as T
 from rvel_mcmc_b200 import _abi, driver
 
 W = int(sys.argv[1]) if len(sys.argv) > 1 else 28416
-N = int(sys.argv[2]) if len(sys.argv) > 2 else 6000
+N = int(sys.argv[2]) if len(sys.argv) > 2 else 4000
 out_dir = sys.argv[3] if len(sys.argv) > 3 else os.path.join(ROOT, "gpurun_out")
 ctx = _abi.Context(0)
 obs = T.load_vels("HD155358.vels")
@@ -39,6 +39,7 @@ for q in range(4):
     theta, lnp = r["theta"], r["lnp"]
     acc += float(r["n_accept"].mean())
     quarters.append(theta.copy())
+    print("quarter %d done after %.1f s, std %s" % (q + 1, time.perf_counter() - t0, np.array2string(theta.std(axis=0), precision=3)), flush=True)
 sec = time.perf_counter() - t0
 ks34 = driver.calc_kstatistic(quarters[2], quarters[3])
 ks14 = driver.calc_kstatistic(quarters[0], quarters[3])

@@ -23,7 +23,7 @@ for W in sizes:
     lp = torch.empty(W, dtype=torch.float64, device="cuda"); st = torch.empty(W, dtype=torch.int32, device="cuda")
     g = torch.empty((W, 10), dtype=torch.float64, device="cuda"); h = torch.empty((W, 10, 10), dtype=torch.float64, device="cuda")
     ref = None
-    for layout in (1, 0):
+    for layout in [int(x) for x in os.environ.get("LAYOUTS", "1,0").split(",")]:
         m.set_option("var_layout", layout)
         m.loglik_d_dd_dev(oh, theta.data_ptr(), min(W, 64), lp.data_ptr(), g.data_ptr(), h.data_ptr(), st.data_ptr(), s)
         torch.cuda.synchronize()
