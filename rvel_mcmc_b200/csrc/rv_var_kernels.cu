@@ -193,6 +193,8 @@ int var_threads_needed(int P, int nv) {
 
 // layout: 0 = automatic (set-per-lane kernel where it exists: one or two planets), 1 = thread per (set, planet)
 cudaError_t launch_var(const VarArgs& a, int P, int D, int nv, int layout, int num_sms, cudaStream_t stream) {
+    if (layout == 2 && P == 2 && D == 2 && var2_min_threads(nv) <= 96)       // tuning: 168 registers -> 3 CTAs per SM
+        return launch_var2_one<2, 2, 96, 168>(a, nv, num_sms, stream);
     if (layout == 0 && var2_supported(P, nv)) {
         const int nt = var2_min_threads(nv);
         if (P == 1 && D == 2 && nt <= 64) return launch_var2_one<1, 2, 64, 168>(a, nv, num_sms, stream);
