@@ -127,7 +127,7 @@ def oracle_batch(obs, theta, nthreads):
 # ---------------------------------------------------------------------------------------------------------------
 # ESS/s (BASELINE metric, second half): the three device samplers from an equilibrated start
 
-def run_ess(ctx, model, oh, rank, world, dist, dev, rows, torch, budgets=(80.0, 50.0, 90.0)):
+def run_ess(ctx, model, oh, rank, world, dist, dev, rows, torch, budgets=(150.0, 80.0, 130.0)):
     from rvel_mcmc_b200.samplers import ess
     from rvel_mcmc_b200 import driver
     if not os.path.exists(EQUILIBRATED):
@@ -181,7 +181,7 @@ def run_ess(ctx, model, oh, rank, world, dist, dev, rows, torch, budgets=(80.0, 
               {"accept_rate": float(r["n_accept"].mean() / n), "a": 2.0})
     del r
     # Metropolis-Hastings: proposal scale 0.25 x the posterior standard deviations of the equilibrated ensemble
-    W = min(len(eq), slots // 2)
+    W = min(len(eq), slots)                 # two waves of (walker, leg) items per step: the long tail of one wave overlaps the next
     t0 = time.perf_counter()
     model.mh_run(oh, eq[:W], post_std, 0.25, 10, seed=1, record_chain=False)
     n = sized("mh", budgets[1], time.perf_counter() - t0)
@@ -190,8 +190,9 @@ def run_ess(ctx, model, oh, rank, world, dist, dev, rows, torch, budgets=(80.0, 
     summarise("mh", r["chain"], time.perf_counter() - t0, W * (n + 1),
               {"accept_rate": float(r["n_accept"].mean() / n), "step_size": 0.25, "scales": "posterior std"})
     del r
-    # SMALA with the reference's step size and SoftAbs constant ((Ex)HD155358.ipynb:640): one wave of variational CTAs
-    W = ctx.device_info()["sm_count"] * 3 // 2
+    # SMALA with the reference's step size and SoftAbs constant ((Ex)HD155358.ipynb:640): two waves of warp groups
+    # (4 groups = 4 walker legs per SM resident in var2_kernel)
+    W = ctx.device_info()["sm_count"] * 4
     t0 = time.perf_counter()
     model.smala_run(oh, eq[:W], 0.025, 1.4, 10, seed=1, record_chain=False)
     n = sized("smala", budgets[2], time.perf_counter() - t0)
@@ -207,7 +208,7 @@ def run_ess(ctx, model, oh, rank, world, dist, dev, rows, torch, budgets=(80.0, 
 # value + gradient + Hessian (State.get_logp_d_dd): var_kernel throughput and roofline
 
 def run_var(ctx, model, oh, dev, peak, torch):
-    W = ctx.device_info()["sm_count"] * 3 // 2 * 8          # eight waves of CTAs
+    W = ctx.device_info()["sm_count"] * 2 * 8              # eight waves of warp groups (4 walker legs per SM resident)
     th = torch.from_numpy(walker_ball(W, 4242)).to(dev)
     lp = torch.empty(W, dtype=torch.float64, device=dev); st = torch.empty(W, dtype=torch.int32, device=dev)
     g = torch.empty((W, 10), dtype=torch.float64, device=dev); h = torch.empty((W, 10, 10), dtype=torch.float64, device=dev)
@@ -356,7 +357,7 @@ def main():
     ap.add_argument("--ess", action="store_true", help="(default on; kept for compatibility)")
     ap.add_argument("--ess-rows", type=int, default=2000, help="recorded rows (= sampler steps) per ESS run (fewer if the "
                                                                "per-sampler time budget says so; the line reports it)")
-    ap.add_argument("--ess-budget", default="80,50,90", help="seconds for the stretch, MH and SMALA ESS runs")
+    ap.add_argument("--ess-budget", default="150,80,130", help="seconds for the stretch, MH and SMALA ESS runs")
     ap.add_argument("--no-var", action="store_true")
     ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the sharded stretch block")
     ap.add_argument("--sharded-steps", type=int, default=6)

@@ -1,18 +1,20 @@
-// rv_var2.cuh -- value + gradient + Hessian of the RV log-likelihood, "one lane per variational set" layout.
+// rv_var2.cuh -- value + gradient + Hessian of the RV log-likelihood, "warp-group per walker leg" layout.
 //
 // Same contract as rv_var.cuh (State.get_logp_d_dd, state.py:290-294; setup_sim_vars state.py:229-248; get_chi2_d_dd
-// state.py:253-285; one CTA per (walker, leg), all sets share one IAS15 step sequence, real-only step-size norm), but a
-// different mapping for systems of one or two planets:
-//   * every lane owns a whole variational SET -- all P planets of it -- so a second-order lane needs nothing from the
-//     other second-order lanes: pair terms are computed once (Newton's third law), its own predicted positions never
-//     leave its registers;
-//   * the real set and the nv first-order sets ("cheap" sets) live in ONE producer warp.  They do not depend on the
-//     second-order sets, so that warp runs ahead inside a predictor-corrector iteration: per Gauss-Radau substep it
-//     publishes its predicted positions and star sums to shared memory and signals a NAMED barrier (bar.arrive); the
-//     second-order warps wait on that barrier only (bar.sync) -- no CTA-wide barrier per substep;
-//   * the only CTA-wide barriers are the convergence monitor (once per iteration) and the once-per-step bookkeeping.
-// The once-per-step state (x0, carries, e, and the rejected-step history br / er) lives in shared memory, strided per lane.
-// Written against an executor like rv_var.cuh, so the CPU test-suite runs the same source sequentially.
+// state.py:253-285; one item = one leg of one walker, all sets share one IAS15 step sequence, real-only step-size
+// norm), for systems of one or two planets.  The mapping:
+//   * a GROUP of warps integrates one (walker, leg); a CTA holds several independent groups, so the register file is
+//     allocated in full 128-thread units while each leg only occupies the warps it needs (96 threads for HD155358);
+//   * second-order ("so") lanes own a whole variational SET -- all P planets of it: nothing is exchanged between so
+//     lanes, pair terms are computed once (Newton's third law), their predicted positions never leave the registers;
+//   * the real set and the nv first-order sets live in ONE producer warp, one lane per (set, planet).  They do not
+//     depend on the second-order sets and carry half the work per lane, so the producer runs ahead of the so warps inside
+//     a predictor-corrector iteration: per Gauss-Radau substep it publishes its predicted positions and star sums to
+//     shared memory and arrives on that substep's mbarrier; the so warps wait on the mbarrier only;
+//   * group-wide barriers (named barriers, one id per group) remain for the convergence monitor (once per iteration) and
+//     the once-per-step bookkeeping; nothing is CTA-wide.
+// The once-per-step state (x0, carries, e, and the rejected-step history br / er) lives in shared memory, strided per
+// planet slot.  Written against an executor like rv_var.cuh, so the CPU test-suite runs the same source sequentially.
 #pragma once
 #include "rv_var.cuh"
 
@@ -21,149 +23,155 @@ namespace rv {
 struct Var2Layout {
     int P, D, nv, n2, nsets;
     int nso_warps;     // warps of second-order lanes (lane t of these warps owns second-order set t)
-    int NT;            // threads launched = 32 * (nso_warps + 1); the last warp is the producer (real + first-order)
-    int nslots;        // lanes that own a set: n2 + nv + 1 (slot = t for second-order, n2 + lane for the producer warp)
-    int CB;            // doubles per cheap-set block in a buffer: P*D positions + D star sum
-    int cstride;       // doubles per buffer: (nv + 1) * CB
-    int o_cbuf, o_vx, o_dm, o_red, o_real, o_state, total;   // offsets in doubles
+    int NT;            // threads of one group = 32 * (nso_warps + 1); the last warp is the producer
+    int nps;           // planet slots: nsets * P (so lane t, planet p -> p * n2 + t; producer lane (s, p) -> n2 * P + s * P + p)
+    int CB;            // doubles per producer-set block in a buffer: P*D positions + D star sum
+    int cstride;       // doubles per buffer: (nv + 1) * CB, rounded up to even
+    int o_cbuf, o_dm, o_red, o_real, o_mbar, o_state, total;   // offsets in doubles (per group)
 };
 constexpr int VAR2_STATE_PER_COORD = 24;   // x0, csx, csv, e[7], br[7], er[7]
 
-// NT = 0: the smallest CTA that fits; otherwise the launched size (a multiple of 32, at least var2_min_threads)
 RV_HD int var2_min_threads(int nv) { return 32 * ((nv * (nv + 1) / 2 + 31) / 32 + 1); }
+// NT = 0: the smallest group that fits; otherwise the launched group size (a multiple of 32, >= var2_min_threads)
 RV_HD Var2Layout var2_layout(int P, int D, int nv, int NT = 0) {
     Var2Layout L;
     L.P = P; L.D = D; L.nv = nv; L.n2 = nv * (nv + 1) / 2; L.nsets = 1 + nv + L.n2;
     L.NT = NT > 0 ? NT : var2_min_threads(nv);
     L.nso_warps = L.NT / 32 - 1;
-    L.nslots = L.n2 + nv + 1;
+    L.nps = L.nsets * P;
     L.CB = P * D + D;
     L.cstride = (nv + 1) * L.CB;
     if (L.cstride & 1) L.cstride++;
     int o = 0;
-    L.o_cbuf = o; o += 8 * L.cstride;                       // buffer 0: positions at x0; 1..7: predicted at substep n
-    L.o_vx = o; o += L.nsets * P; if (o & 1) o++;
+    L.o_cbuf = o; o += 8 * L.cstride;      // buffer 0: positions at x0; 1..7: predicted at substep n (1.. reused for the epoch exchange)
     L.o_dm = o; o += (nv > 0 ? nv : 1) * P; if (o & 1) o++;
-    L.o_red = o; o += 2 * 2 * 32 + 2;
-    L.o_real = o; o += 2 * P * D; if (o & 1) o++;           // the real lane's last force and b6 (step-size control)
-    L.o_state = o; o += VAR2_STATE_PER_COORD * P * D * L.nslots;
+    L.o_red = o; o += 2 * 2 * 8 + 2;        // ping-pong group maxima (up to 8 warps) + the item broadcast slot
+    L.o_real = o; o += P * D; if (o & 1) o++;      // the real lanes' last force (step-size control)
+    L.o_mbar = o; o += 8;                   // seven substep mbarriers (8 bytes each)
+    L.o_state = o; o += VAR2_STATE_PER_COORD * D * L.nps;
+    if (o & 1) o++;
     L.total = o;
     return L;
 }
-RV_HD bool var2_supported(int P, int nv) { return P <= 2 && nv + 1 <= 32; }
+// one or two planets; real + first-order sets must fit one warp at one lane per (set, planet); at most 8 warps per group
+RV_HD bool var2_supported(int P, int nv) { return P <= 2 && (nv + 1) * P <= 32 && var2_min_threads(nv) <= 256; }
 
 template <int P, int D>
 struct Var2Thread {
     static constexpr int NC = P * D;
-    int tid, role;                 // role: 0 real, 1 first-order, 2 second-order, -1 idle
-    int set, slot, pa, pb;
-    int ou, oa, ob;                // block offsets inside a cheap buffer: own (producer lanes), parents (second-order)
-    double x0c[NC], v0[NC], a0[NC], ha0[NC];
+    int tid;                       // thread index inside the group
+    int role;                      // 0 real, 1 first-order (producer warp; own D coordinates), 2 second-order (all P*D), -1 idle
+    int set, planet, pa, pb;
+    int slot0;                     // planet slot of coordinate block 0 (so lanes: planet p at slot0 + p * n2)
+    int ou, oa, ob;                // block offsets inside a producer buffer: own set, parents
+    double x0c[NC], v0[NC], a0[NC];
     double q[7][NC];               // b between step attempts, g inside the predictor-corrector loop
     double xn[NC];
-    double mon_g, mon_a;           // convergence-monitor contributions of the last substep-7
-    double acc;                    // running chi2 / d[a] / dd[a][b]
+    double mon_g, mon_a;           // convergence-monitor contributions of the last substep 7
+    double acc;                    // running chi2 / d[a] / dd[a][b] (planet-0 lane of a producer set; so lanes)
 };
 
 template <int P, int D>
 RV_D void var2_assign(Var2Thread<P, D>& th, int tid, const Var2Layout& L) {
-    th.tid = tid; th.role = -1; th.set = 0; th.slot = 0; th.pa = th.pb = 0;
+    th.tid = tid; th.role = -1; th.set = 0; th.planet = 0; th.pa = th.pb = 0; th.slot0 = 0;
     const int warp = tid >> 5, lane = tid & 31;
     if (warp < L.nso_warps) {
         if (tid < L.n2) {
-            th.role = 2; th.set = 1 + L.nv + tid; th.slot = tid;
+            th.role = 2; th.set = 1 + L.nv + tid; th.slot0 = tid;
             int a = 0;
             while ((a + 1) * (a + 2) / 2 <= tid) a++;
             th.pa = a; th.pb = tid - a * (a + 1) / 2;
         }
-    } else if (lane <= L.nv) {
-        th.role = lane == 0 ? 0 : 1; th.set = lane; th.slot = L.n2 + lane;
-        th.pa = th.pb = lane == 0 ? 0 : lane - 1;
+    } else if (lane < (L.nv + 1) * P) {
+        th.set = lane / P; th.planet = lane - th.set * P;
+        th.role = th.set == 0 ? 0 : 1;
+        th.slot0 = L.n2 * P + lane;
+        th.pa = th.pb = th.set == 0 ? 0 : th.set - 1;
     }
     th.ou = th.set * L.CB;
     th.oa = (1 + th.pa) * L.CB; th.ob = (1 + th.pb) * L.CB;
 }
 
-// ---- forces ------------------------------------------------------------------------------------------------------
-// real set: a_i = -m0 f(x_i + S) - sum_{j != i} m_j f(x_i - x_j), f(d) = d / r^3, S = sum mu_j x_j (= -r_star)
+// ---- forces on ONE planet (producer lanes) -------------------------------------------------------------------------
+// real set: a_p = -m0 f(x_p + S) - sum_{j != p} m_j f(x_p - x_j), f(d) = d / r^3, S = sum mu_j x_j (= -r_star)
 template <int P, int D>
-RV_D void var2_force_real(const double (&x)[P * D], const double (&S)[D], const VarUniform<P>& u, double (&an)[P * D]) {
+RV_D void var2_force_real_planet(int p, const double* __restrict__ X0, const double (&S)[D], const VarUniform<P>& u,
+                                 double (&an)[P * D]) {
+    double xp[D];
 #pragma unroll
-    for (int i = 0; i < P; i++) {
-        double ds[D], r2 = 0.0;
+    for (int d = 0; d < D; d++) {
+        xp[d] = X0[d];
 #pragma unroll
-        for (int d = 0; d < D; d++) { ds[d] = x[i * D + d] + S[d]; r2 = fma(ds[d], ds[d], r2); }
-        const double y = rinv1(r2);
-        const double k = -u.gm0 * (y * y * y);
-#pragma unroll
-        for (int d = 0; d < D; d++) an[i * D + d] = k * ds[d];
+        for (int k = 1; k < P; k++) xp[d] = (p == k) ? X0[k * D + d] : xp[d];
     }
+    double ds[D], r2 = 0.0;
 #pragma unroll
-    for (int i = 0; i < P; i++)
+    for (int d = 0; d < D; d++) { ds[d] = xp[d] + S[d]; r2 = fma(ds[d], ds[d], r2); }
+    double y = rinv1(r2);
+    double k = -u.gm0 * (y * y * y);
 #pragma unroll
-        for (int j = i + 1; j < P; j++) {
-            double dp[D], r2 = 0.0;
+    for (int d = 0; d < D; d++) an[d] = k * ds[d];
 #pragma unroll
-            for (int d = 0; d < D; d++) { dp[d] = x[i * D + d] - x[j * D + d]; r2 = fma(dp[d], dp[d], r2); }
-            const double y = rinv1(r2), r3 = y * y * y;
-            const double ki = -u.gm[j] * r3, kj = u.gm[i] * r3;
+    for (int j = 0; j < P; j++) {
+        if (P == 1) break;
+        double dp[D];
+        r2 = 0.0;
 #pragma unroll
-            for (int d = 0; d < D; d++) {
-                an[i * D + d] = fma(ki, dp[d], an[i * D + d]);
-                an[j * D + d] = fma(kj, dp[d], an[j * D + d]);
-            }
-        }
+        for (int d = 0; d < D; d++) { dp[d] = xp[d] - X0[j * D + d]; r2 = fma(dp[d], dp[d], r2); }
+        y = rinv1(j == p ? 1.0 : r2);
+        k = (j == p) ? 0.0 : -u.gm[j] * (y * y * y);
+#pragma unroll
+        for (int d = 0; d < D; d++) an[d] = fma(k, dp[d], an[d]);
+    }
 }
 
-// first-order set U with mass variations dmu[j] (= d mu_j):  da_i = -sum_j { m_j Df[U_ij] + dm_j f(d_ij) },
-// Df[u] = u / r^3 - 3 d (d.u) / r^5; star terms with d = x0_i + S, u = xu_i + SU, dm_star = 0
+// first-order set U with mass variations dmu[j] (= d mu_j):  da_p = -sum_j { m_j Df[U_pj] + dm_j f(d_pj) },
+// Df[u] = u / r^3 - 3 d (d.u) / r^5; star terms with d = x0_p + S, u = xu_p + SU, dm_star = 0
 template <int P, int D>
-RV_D void var2_force_first(const double (&xu)[P * D], const double* __restrict__ X0, const double (&S)[D],
-                           const double (&SU)[D], const double* __restrict__ dmu, const VarUniform<P>& u,
-                           double (&an)[P * D]) {
-    double x0[P][D];
+RV_D void var2_force_first_planet(int p, const double* __restrict__ X0, const double* __restrict__ XU, const double (&S)[D],
+                                  const double (&SU)[D], const double* __restrict__ dmu, const VarUniform<P>& u,
+                                  double (&an)[P * D]) {
+    double x0p[D], xup[D];
 #pragma unroll
-    for (int i = 0; i < P; i++)
+    for (int d = 0; d < D; d++) {
+        x0p[d] = X0[d]; xup[d] = XU[d];
 #pragma unroll
-        for (int d = 0; d < D; d++) x0[i][d] = X0[i * D + d];
-#pragma unroll
-    for (int i = 0; i < P; i++) {
+        for (int k = 1; k < P; k++) { x0p[d] = (p == k) ? X0[k * D + d] : x0p[d]; xup[d] = (p == k) ? XU[k * D + d] : xup[d]; }
+    }
+    {
         double dd[D], U[D], r2 = 0.0, du = 0.0;
 #pragma unroll
         for (int d = 0; d < D; d++) {
-            dd[d] = x0[i][d] + S[d]; U[d] = xu[i * D + d] + SU[d];
+            dd[d] = x0p[d] + S[d]; U[d] = xup[d] + SU[d];
             r2 = fma(dd[d], dd[d], r2); du = fma(dd[d], U[d], du);
         }
         const double y = rinv1(r2), y2 = y * y, r3i = y * y2, r5i = r3i * y2;
         const double kU = -u.gm0 * r3i, kd = u.gm0 * 3.0 * r5i * du;
 #pragma unroll
-        for (int d = 0; d < D; d++) an[i * D + d] = fma(kU, U[d], kd * dd[d]);
+        for (int d = 0; d < D; d++) an[d] = fma(kU, U[d], kd * dd[d]);
     }
 #pragma unroll
-    for (int i = 0; i < P; i++)
+    for (int j = 0; j < P; j++) {
+        if (P == 1) break;
+        double dd[D], U[D], r2 = 0.0, du = 0.0;
 #pragma unroll
-        for (int j = i + 1; j < P; j++) {
-            double dd[D], U[D], r2 = 0.0, du = 0.0;
-#pragma unroll
-            for (int d = 0; d < D; d++) {
-                dd[d] = x0[i][d] - x0[j][d]; U[d] = xu[i * D + d] - xu[j * D + d];
-                r2 = fma(dd[d], dd[d], r2); du = fma(dd[d], U[d], du);
-            }
-            const double y = rinv1(r2), y2 = y * y, r3i = y * y2, r5i = r3i * y2;
-            const double c5du = -3.0 * r5i * du;
-            // side i uses (m_j, dm_j), side j uses (m_i, dm_i) with the opposite sign
-            const double kUi = u.gm[j] * r3i, kdi = fma(u.gm[j], c5du, dmu[j] * u.gm0 * r3i);
-            const double kUj = u.gm[i] * r3i, kdj = fma(u.gm[i], c5du, dmu[i] * u.gm0 * r3i);
-#pragma unroll
-            for (int d = 0; d < D; d++) {
-                an[i * D + d] -= fma(kUi, U[d], kdi * dd[d]);
-                an[j * D + d] += fma(kUj, U[d], kdj * dd[d]);
-            }
+        for (int d = 0; d < D; d++) {
+            dd[d] = x0p[d] - X0[j * D + d]; U[d] = xup[d] - XU[j * D + d];
+            r2 = fma(dd[d], dd[d], r2); du = fma(dd[d], U[d], du);
         }
+        const double y = rinv1(j == p ? 1.0 : r2), y2 = y * y, r3i = y * y2, r5i = r3i * y2;
+        const double mj = (j == p) ? 0.0 : u.gm[j], dmj = (j == p) ? 0.0 : dmu[j] * u.gm0;
+        const double kU = mj * r3i;
+        const double kd = fma(mj * (-3.0 * r5i), du, dmj * r3i);
+#pragma unroll
+        for (int d = 0; d < D; d++) an[d] -= fma(kU, U[d], kd * dd[d]);
+    }
 }
 
-// second-order set U with parents A, B:  d2a_i = -sum_j { m_j (Df[U] + D2f[A,B]) + dm_j^a Df[B] + dm_j^b Df[A] },
-// D2f[u,w] = -3 [u (d.w) + w (d.u) + d (u.w)] / r^5 + 15 d (d.u)(d.w) / r^7          (d2 m = 0)
+// ---- force on a whole second-order set (so lanes) ------------------------------------------------------------------
+// d2a_i = -sum_j { m_j (Df[U] + D2f[A,B]) + dm_j^a Df[B] + dm_j^b Df[A] },  (d2 m = 0)
+// D2f[u,w] = -3 [u (d.w) + w (d.u) + d (u.w)] / r^5 + 15 d (d.u)(d.w) / r^7.  X0 / XA / XB: producer blocks (positions of
+// the real set and of the two parents, each followed by its star sum).
 template <int P, int D>
 RV_D void var2_force_second(const double (&xu)[P * D], const double* __restrict__ X0, const double* __restrict__ XA,
                             const double* __restrict__ XB, const double* __restrict__ dma, const double* __restrict__ dmb,
@@ -234,16 +242,15 @@ RV_D void var2_force_second(const double (&xu)[P * D], const double* __restrict_
         }
 }
 
-// ---- predictor / corrector over the lane's NC coordinates ----------------------------------------------------------
-template <int P, int D>
+// ---- predictor / corrector over the first N coordinates of a lane ------------------------------------------------------
+template <int N, int P, int D>
 RV_D void var2_predict_positions(Var2Thread<P, D>& th, int n, double dt) {
-    constexpr int NC = P * D;
     const double dth = dt * rvtabm::H[n];
     const double c0 = rvtabm::PG[n][0], c1 = rvtabm::PG[n][1], c2 = rvtabm::PG[n][2], c3 = rvtabm::PG[n][3],
                  c4 = rvtabm::PG[n][4], c5 = rvtabm::PG[n][5], c6 = rvtabm::PG[n][6];
 #pragma unroll
-    for (int c = 0; c < NC; c++) {
-        double p0 = fma(c0, th.q[0][c], th.ha0[c]);
+    for (int c = 0; c < N; c++) {
+        double p0 = fma(c0, th.q[0][c], 0.5 * th.a0[c]);
         p0 = fma(c1, th.q[1][c], p0);
         p0 = fma(c2, th.q[2][c], p0);
         double p1 = c3 * th.q[3][c];
@@ -255,20 +262,26 @@ RV_D void var2_predict_positions(Var2Thread<P, D>& th, int n, double dt) {
     }
 }
 
-template <int n, int P, int D>
+template <int n, int N, int P, int D>
 RV_D void var2_corrector_n(Var2Thread<P, D>& th, const double (&an)[P * D]) {
-    constexpr int NC = P * D;
     double mg = 0.0, ma = 0.0;
 #pragma unroll
-    for (int c = 0; c < NC; c++) {
+    for (int c = 0; c < N; c++) {
         const double gk = an[c] - th.a0[c];
-        double s0 = gk * rvtab::GA[n], s1 = 0.0;
+        double gn;
+        if (n <= 2) {
+            gn = gk * rvtab::GA[n];
+            if (n == 2) gn = fma(-th.q[0][c], rvtab::GB[n][0], gn);
+        } else {
+            double s0 = gk * rvtab::GA[n], s1 = -th.q[1][c] * rvtab::GB[n][1];
 #pragma unroll
-        for (int i = 0; i < n - 1; i++) {
-            if (i & 1) s1 = fma(-th.q[i][c], rvtab::GB[n][i], s1);
-            else s0 = fma(-th.q[i][c], rvtab::GB[n][i], s0);
+            for (int i = 0; i < n - 1; i++) {
+                if (i == 1) continue;
+                if (i & 1) s1 = fma(-th.q[i][c], rvtab::GB[n][i], s1);
+                else s0 = fma(-th.q[i][c], rvtab::GB[n][i], s0);
+            }
+            gn = s0 + s1;
         }
-        const double gn = s0 + s1;
         if (n == 7) {
             const double ak = fabs(an[c]), dg = fabs(gn - th.q[6][c]);
             if (is_normal(ak) && ak > ma) ma = ak;
@@ -278,21 +291,21 @@ RV_D void var2_corrector_n(Var2Thread<P, D>& th, const double (&an)[P * D]) {
     }
     if (n == 7) { th.mon_g = mg; th.mon_a = ma; }
 }
-template <int P, int D>
+template <int N, int P, int D>
 RV_D void var2_corrector(Var2Thread<P, D>& th, int n, const double (&an)[P * D]) {
     switch (n) {
-        case 1: var2_corrector_n<1>(th, an); break;
-        case 2: var2_corrector_n<2>(th, an); break;
-        case 3: var2_corrector_n<3>(th, an); break;
-        case 4: var2_corrector_n<4>(th, an); break;
-        case 5: var2_corrector_n<5>(th, an); break;
-        case 6: var2_corrector_n<6>(th, an); break;
-        default: var2_corrector_n<7>(th, an); break;
+        case 1: var2_corrector_n<1, N>(th, an); break;
+        case 2: var2_corrector_n<2, N>(th, an); break;
+        case 3: var2_corrector_n<3, N>(th, an); break;
+        case 4: var2_corrector_n<4, N>(th, an); break;
+        case 5: var2_corrector_n<5, N>(th, an); break;
+        case 6: var2_corrector_n<6, N>(th, an); break;
+        default: var2_corrector_n<7, N>(th, an); break;
     }
 }
 
-// Initial conditions of every planet of the lane's set: the jet of the barycentric state with respect to the set's
-// parameters (state.py:229-248: add_variation + vary + move_to_com).
+// Initial conditions of the lane's coordinates: the jet of the barycentric state with respect to the set's parameters
+// (state.py:229-248: add_variation + vary + move_to_com).  Producer lanes keep their own planet in block 0.
 template <int P, int D>
 RV_D void var2_initial(const Var2Thread<P, D>& th, const Model* __restrict__ md, const double (&el)[P][NELEM],
                        double (&x0)[P * D], double (&v0)[P * D]) {
@@ -322,25 +335,33 @@ RV_D void var2_initial(const Var2Thread<P, D>& th, const Model* __restrict__ md,
             x0[i * D + d] = th.role == 0 ? x.v : (th.role == 1 ? x.d1 : x.d12);
             v0[i * D + d] = th.role == 0 ? v.v : (th.role == 1 ? v.d1 : v.d12);
         }
+    if (th.role <= 1) {      // producer lane: its own planet moves to block 0
+#pragma unroll
+        for (int d = 0; d < D; d++) {
+            double xs = x0[d], vs = v0[d];
+#pragma unroll
+            for (int k = 1; k < P; k++) { xs = (th.planet == k) ? x0[k * D + d] : xs; vs = (th.planet == k) ? v0[k * D + d] : vs; }
+            x0[d] = xs; v0[d] = vs;
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// The CTA algorithm.  Exec provides (device / sequential host emulation):
-//   each(f)            run f(Var2Thread&) for every thread of the CTA
-//   sync()             CTA barrier
+// The group algorithm.  Exec provides (device / sequential host emulation):
+//   each(f)            run f(Var2Thread&) for every thread of the group
+//   sync()             group barrier
 //   producer_sync()    barrier among the lanes of the producer warp (no-op for the others)
-//   signal(n)          producer warp: arrive on named barrier n (after publishing substep n)
-//   wait(n)            second-order warps: wait on named barrier n
-//   stage_max / read_max / fetch / add_work   as in rv_var.cuh
+//   signal(n)          producer warp: substep n is published
+//   wait(n)            second-order warps: wait until substep n is published
+//   stage_max / read_max / fetch / add_work   as in rv_var.cuh (group-wide)
 template <int P, int D, class Exec>
 RV_D void var2_run_items(Exec& ex, const VarArgs& a, const Var2Layout& L, double* __restrict__ sm) {
     constexpr int NC = P * D;
-    constexpr int SPC = VAR2_STATE_PER_COORD;
     const Model* __restrict__ md = a.model;
     const int nv = md->nvars;
-    const int NS = L.nslots;
+    const int NPS = L.nps, n2 = L.n2;
     double* const cbuf = sm + L.o_cbuf;
-    double* const vxs = sm + L.o_vx;
+    double* const vxs = cbuf + L.cstride;          // the epoch exchange reuses the substep buffers (dead between steps)
     double* const dm = sm + L.o_dm;
     double* const realv = sm + L.o_real;
     double* const state = sm + L.o_state;
@@ -349,9 +370,15 @@ RV_D void var2_run_items(Exec& ex, const VarArgs& a, const Var2Layout& L, double
     VarUniform<P> u;
     u.gm0 = m0;
     u.epsilon = md->epsilon;
-    // per-lane state in shared memory: entry k of coordinate c at state[(k * NC + c) * NS + slot]
-    auto ST = [&](const Var2Thread<P, D>& th, int k, int c) -> double& { return state[(size_t)(k * NC + c) * NS + th.slot]; };
+    // per-coordinate state in shared memory: entry k of coordinate (block p, axis d) of a lane at
+    // state[(k * D + d) * NPS + slot], slot = slot0 + p * n2 for so lanes, slot0 for producer lanes (block 0 only)
+    auto ST = [&](const Var2Thread<P, D>& th, int k, int c) -> double& {
+        const int p = c / D, d = c - p * D;
+        return state[(size_t)(k * D + d) * NPS + th.slot0 + p * n2];
+    };
     enum { K_X0 = 0, K_CSX = 1, K_CSV = 2, K_E = 3, K_BR = 10, K_ER = 17 };
+    // a lane's coordinate count: producer lanes carry one planet, so lanes the whole set
+    auto NCOF = [](const Var2Thread<P, D>& th) { return th.role == 2 ? NC : D; };
 
     ex.each([&](Var2Thread<P, D>& th) {
         if (th.tid < nv * P) {
@@ -393,53 +420,46 @@ RV_D void var2_run_items(Exec& ex, const VarArgs& a, const Var2Layout& L, double
             const double emd = md->hill_factor * hill;
             u.min2 = emd * emd;
 
-            // publish the producer lanes' positions x (and star sums) into buffer `b`: two phases around a producer-warp sync
+            // Producer lanes publish their planet's position into buffer b (x0 or the predicted xn), and -- after a
+            // producer-warp sync -- the planet-0 lane of each set adds the set's star sum:
+            //   real set   S  = sum_j mu_j x_j            first-order set a   SA = sum_j (mu_j xa_j + dmu^a_j x_j)
             auto publish_positions = [&](int b, bool from_xn) {
                 double* Xw = cbuf + b * L.cstride;
                 ex.each([&](Var2Thread<P, D>& th) {
                     if (th.role != 0 && th.role != 1) return;
-                    double* blk = Xw + th.ou;
+                    double* blk = Xw + th.ou + th.planet * D;
 #pragma unroll
-                    for (int c = 0; c < NC; c++) blk[c] = from_xn ? th.xn[c] : ST(th, K_X0, c);
-                    if (th.role == 0) {
-#pragma unroll
-                        for (int d = 0; d < D; d++) {
-                            double s = 0.0;
-#pragma unroll
-                            for (int j = 0; j < P; j++) s = fma(u.mu[j], blk[j * D + d], s);
-                            blk[NC + d] = s;
-                        }
-                    }
+                    for (int d = 0; d < D; d++) blk[d] = from_xn ? th.xn[d] : ST(th, K_X0, d);
                 });
                 ex.producer_sync();
                 ex.each([&](Var2Thread<P, D>& th) {
-                    if (th.role != 1) return;
+                    if ((th.role != 0 && th.role != 1) || th.planet != 0) return;
                     double* blk = Xw + th.ou;
                     const double* dma = dm + th.pa * P;
 #pragma unroll
                     for (int d = 0; d < D; d++) {
                         double s = 0.0;
 #pragma unroll
-                        for (int j = 0; j < P; j++) s = fma(u.mu[j], blk[j * D + d], fma(dma[j], Xw[j * D + d], s));
+                        for (int j = 0; j < P; j++) {
+                            s = fma(u.mu[j], blk[j * D + d], s);
+                            if (th.role == 1) s = fma(dma[j], Xw[j * D + d], s);
+                        }
                         blk[NC + d] = s;
                     }
                 });
             };
-            // force on the lane's set at positions x (own) with the producer data of buffer b
+            // force on the lane's coordinates at positions x with the producer data of buffer b.  Producer lanes need
+            // their own set's star sum, which the planet-0 lane wrote after the producer sync: callers sync again first.
             auto force = [&](const Var2Thread<P, D>& th, int b, const double (&x)[NC], double (&an)[NC]) {
                 const double* Xr = cbuf + b * L.cstride;
                 if (th.role == 2) {
                     var2_force_second<P, D>(x, Xr, Xr + th.oa, Xr + th.ob, dm + th.pa * P, dm + th.pb * P, u, an);
-                } else if (th.role == 1) {
+                } else {
                     double S[D], SU[D];
 #pragma unroll
                     for (int d = 0; d < D; d++) { S[d] = Xr[NC + d]; SU[d] = Xr[th.ou + NC + d]; }
-                    var2_force_first<P, D>(x, Xr, S, SU, dm + th.pa * P, u, an);
-                } else {
-                    double S[D];
-#pragma unroll
-                    for (int d = 0; d < D; d++) S[d] = Xr[NC + d];
-                    var2_force_real<P, D>(x, S, u, an);
+                    if (th.role == 1) var2_force_first_planet<P, D>(th.planet, Xr, Xr + th.ou, S, SU, dm + th.pa * P, u, an);
+                    else var2_force_real_planet<P, D>(th.planet, Xr, S, u, an);
                 }
             };
 
@@ -448,14 +468,16 @@ RV_D void var2_run_items(Exec& ex, const VarArgs& a, const Var2Layout& L, double
                 double x0[NC], v0[NC];
                 var2_initial(th, md, el, x0, v0);
                 th.acc = 0.0; th.mon_g = 0.0; th.mon_a = 0.0;
+                const int nc = NCOF(th);
 #pragma unroll
                 for (int c = 0; c < NC; c++) {
-                    th.v0[c] = v0[c]; th.a0[c] = 0.0; th.ha0[c] = 0.0; th.xn[c] = x0[c]; th.x0c[c] = x0[c];
-                    ST(th, K_X0, c) = x0[c]; ST(th, K_CSX, c) = 0.0; ST(th, K_CSV, c) = 0.0;
+                    th.v0[c] = v0[c]; th.a0[c] = 0.0; th.xn[c] = x0[c]; th.x0c[c] = x0[c];
 #pragma unroll
-                    for (int k = 0; k < 7; k++) {
-                        th.q[k][c] = 0.0;
-                        ST(th, K_E + k, c) = 0.0; ST(th, K_BR + k, c) = 0.0; ST(th, K_ER + k, c) = 0.0;
+                    for (int k = 0; k < 7; k++) th.q[k][c] = 0.0;
+                    if (c < nc) {
+                        ST(th, K_X0, c) = x0[c]; ST(th, K_CSX, c) = 0.0; ST(th, K_CSV, c) = 0.0;
+#pragma unroll
+                        for (int k = 0; k < 7; k++) { ST(th, K_E + k, c) = 0.0; ST(th, K_BR + k, c) = 0.0; ST(th, K_ER + k, c) = 0.0; }
                     }
                 }
             });
@@ -467,18 +489,19 @@ RV_D void var2_run_items(Exec& ex, const VarArgs& a, const Var2Layout& L, double
             LegCursor c;
             c.status = RUN; c.ie = 0; c.n = n; c.attempts = 0; c.tmax = 0.0; c.last_full_dt = 0.0; c.chi2 = 0.0;
 
-            // ---- one IAS15 step attempt of the whole CTA; bit0 accepted, bit1 encounter after the step ----
+            // ---- one IAS15 step attempt of the whole group; bit0 accepted, bit1 encounter after the step ----
             auto attempt = [&]() -> int {
                 n_attempt++;
                 ex.each([&](Var2Thread<P, D>& th) {
                     if (th.role < 0) return;
+                    const int nc = NCOF(th);
                     double x0[NC];
 #pragma unroll
-                    for (int cc = 0; cc < NC; cc++) x0[cc] = ST(th, K_X0, cc);
+                    for (int cc = 0; cc < NC; cc++) x0[cc] = cc < nc ? ST(th, K_X0, cc) : 0.0;
                     force(th, 0, x0, th.a0);
 #pragma unroll
                     for (int cc = 0; cc < NC; cc++) {
-                        th.ha0[cc] = 0.5 * th.a0[cc];
+                        if (cc >= nc) break;
                         th.x0c[cc] = x0[cc] - ST(th, K_CSX, cc);
 #pragma unroll
                         for (int j = 0; j < 7; j++) {      // g from b, in place
@@ -499,27 +522,28 @@ RV_D void var2_run_items(Exec& ex, const VarArgs& a, const Var2Layout& L, double
 #pragma unroll 1
                     for (int nn = 1; nn <= 7; nn++) {
                         // producer warp: predict, publish, signal, then its own force + corrector
-                        ex.each([&](Var2Thread<P, D>& th) { if (th.role == 0 || th.role == 1) var2_predict_positions(th, nn, dt); });
+                        ex.each([&](Var2Thread<P, D>& th) { if (th.role == 0 || th.role == 1) var2_predict_positions<D>(th, nn, dt); });
                         publish_positions(nn, true);
                         ex.signal(nn);
+                        ex.producer_sync();
                         ex.each([&](Var2Thread<P, D>& th) {
                             if (th.role != 0 && th.role != 1) return;
                             double an[NC];
                             force(th, nn, th.xn, an);
-                            var2_corrector(th, nn, an);
+                            var2_corrector<D>(th, nn, an);
                             if (nn == 7 && th.role == 0) {
 #pragma unroll
-                                for (int cc = 0; cc < NC; cc++) realv[cc] = an[cc];
+                                for (int d = 0; d < D; d++) realv[th.planet * D + d] = an[d];
                             }
                         });
                         // second-order warps: predict in registers, wait for the producer's substep, force + corrector
-                        ex.each([&](Var2Thread<P, D>& th) { if (th.role == 2) var2_predict_positions(th, nn, dt); });
+                        ex.each([&](Var2Thread<P, D>& th) { if (th.role == 2) var2_predict_positions<NC>(th, nn, dt); });
                         ex.wait(nn);
                         ex.each([&](Var2Thread<P, D>& th) {
                             if (th.role != 2) return;
                             double an[NC];
                             force(th, nn, th.xn, an);
-                            var2_corrector(th, nn, an);
+                            var2_corrector<NC>(th, nn, an);
                         });
                     }
                     ex.each([&](Var2Thread<P, D>& th) {
@@ -536,8 +560,10 @@ RV_D void var2_run_items(Exec& ex, const VarArgs& a, const Var2Layout& L, double
                 ex.each([&](Var2Thread<P, D>& th) {
                     double mb = 0.0, ma = 0.0;
                     if (th.role >= 0) {
+                        const int nc = NCOF(th);
 #pragma unroll
                         for (int cc = 0; cc < NC; cc++) {
+                            if (cc >= nc) break;
 #pragma unroll
                             for (int k = 0; k < 7; k++) {
                                 double s = 0.0;
@@ -548,20 +574,15 @@ RV_D void var2_run_items(Exec& ex, const VarArgs& a, const Var2Layout& L, double
                         }
                     }
                     if (th.role == 0) {
+                        double v2 = 0.0, x2 = 0.0;
 #pragma unroll
-                        for (int p = 0; p < P; p++) {
-                            double v2 = 0.0, x2 = 0.0;
+                        for (int d = 0; d < D; d++) { v2 = fma(th.v0[d], th.v0[d], v2); x2 = fma(th.xn[d], th.xn[d], x2); }
+                        const bool keep = !(fabs(v2 * dt * dt) < 1e-16 * x2);
 #pragma unroll
-                            for (int d = 0; d < D; d++) {
-                                v2 = fma(th.v0[p * D + d], th.v0[p * D + d], v2); x2 = fma(th.xn[p * D + d], th.xn[p * D + d], x2);
-                            }
-                            const bool keep = !(fabs(v2 * dt * dt) < 1e-16 * x2);
-#pragma unroll
-                            for (int d = 0; d < D; d++) {
-                                const double ak = fabs(realv[p * D + d]), b6 = fabs(th.q[6][p * D + d]);
-                                if (keep && is_normal(ak) && ak > ma) ma = ak;
-                                if (keep && is_normal(b6) && b6 > mb) mb = b6;
-                            }
+                        for (int d = 0; d < D; d++) {
+                            const double ak = fabs(realv[th.planet * D + d]), b6 = fabs(th.q[6][d]);
+                            if (keep && is_normal(ak) && ak > ma) ma = ak;
+                            if (keep && is_normal(b6) && b6 > mb) mb = b6;
                         }
                     }
                     ex.stage_max(th, mb, ma);
@@ -581,8 +602,10 @@ RV_D void var2_run_items(Exec& ex, const VarArgs& a, const Var2Layout& L, double
                         const double q = w.dt / w.dt_last_done;
                         ex.each([&](Var2Thread<P, D>& th) {
                             if (th.role < 0) return;
+                            const int nc = NCOF(th);
 #pragma unroll
                             for (int cc = 0; cc < NC; cc++) {
+                                if (cc >= nc) break;
                                 double _e[7], _b[7], e[7];
 #pragma unroll
                                 for (int k = 0; k < 7; k++) { _e[k] = ST(th, K_ER + k, cc); _b[k] = ST(th, K_BR + k, cc); }
@@ -599,8 +622,10 @@ RV_D void var2_run_items(Exec& ex, const VarArgs& a, const Var2Layout& L, double
                     const double q = w.dt / dt_done;
                     ex.each([&](Var2Thread<P, D>& th) {
                         if (th.role < 0) return;
+                        const int nc = NCOF(th);
 #pragma unroll
                         for (int cc = 0; cc < NC; cc++) {
+                            if (cc >= nc) break;
                             {
                                 const double x = ST(th, K_X0, cc);
                                 double csx = ST(th, K_CSX, cc);
@@ -674,8 +699,12 @@ RV_D void var2_run_items(Exec& ex, const VarArgs& a, const Var2Layout& L, double
                 // epoch reached: star vx of every set, chi2 / d / dd sums (state.py:264-271)
                 ex.each([&](Var2Thread<P, D>& th) {
                     if (th.role < 0) return;
+                    if (th.role == 2) {
 #pragma unroll
-                    for (int p = 0; p < P; p++) vxs[th.set * P + p] = th.v0[p * D];
+                        for (int p = 0; p < P; p++) vxs[th.set * P + p] = th.v0[p * D];
+                    } else {
+                        vxs[th.set * P + th.planet] = th.v0[0];
+                    }
                 });
                 ex.sync();
                 const double svx = var_star_vx<P>(vxs, dm, u, 0, 0, 0, 0, 0, 0);
@@ -685,7 +714,7 @@ RV_D void var2_run_items(Exec& ex, const VarArgs& a, const Var2Layout& L, double
                     const double res = svx - a.orv[ie], er = a.oerr[ie];
                     const double den = er * er * a.npoints;
                     ex.each([&](Var2Thread<P, D>& th) {
-                        if (th.role < 0) return;
+                        if (th.role < 0 || (th.role <= 1 && th.planet != 0)) return;
                         if (th.role == 0) {
                             th.acc += res * res / den;
                         } else if (th.role == 1) {
@@ -706,7 +735,7 @@ RV_D void var2_run_items(Exec& ex, const VarArgs& a, const Var2Layout& L, double
         const int fs = final_status;
         ex.each([&](Var2Thread<P, D>& th) {
             if (th.tid == 0) a.part_status[item] = fs;
-            if (fs == ST_OK && th.role >= 0) a.part[item * L.nsets + th.set] = th.acc;
+            if (fs == ST_OK && th.role >= 0 && (th.role == 2 || th.planet == 0)) a.part[item * L.nsets + th.set] = th.acc;
         });
         ex.add_work(a.work_counters, n_force, n_attempt);
     }

@@ -58,23 +58,39 @@ __global__ void __launch_bounds__(NT, MINB) var_kernel(const VarArgs a, const Va
     var_run_items<P, D>(ex, a, L, sm);
 }
 
-// ---- "one lane per variational set" layout (rv_var2.cuh): producer warp + named barriers ----------------------------
+// ---- "warp group per walker leg" layout (rv_var2.cuh): several independent groups per CTA, producer warp + mbarriers ----
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
 template <int P, int D>
 struct DevVar2Exec {
     Var2Thread<P, D>& th;
-    double* red;                 // [2][64] ping-pong maxima, then the item broadcast slot
-    int parity, nwarps, nt;
-    bool producer;               // this thread's warp is the producer warp (real + first-order sets)
+    double* red;                 // [2][16] ping-pong group maxima, then the item broadcast slot
+    unsigned mbar;               // shared address of the group's seven substep mbarriers
+    int parity, nwarps, nt, bar_id;
+    unsigned round;              // predictor-corrector iterations so far: every substep mbarrier completes once per iteration
+    bool producer;               // this thread's warp is the group's producer warp (real + first-order sets)
     template <class F>
     __device__ __forceinline__ void each(F&& f) { f(th); }
-    __device__ __forceinline__ void sync() { __syncthreads(); }
+    // group barrier: one named barrier per group (id 0 stays free for __syncthreads)
+    __device__ __forceinline__ void sync() { asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nt) : "memory"); }
     __device__ __forceinline__ void producer_sync() { if (producer) __syncwarp(); }
-    // named barriers 1..7 (0 is __syncthreads): the producer warp arrives without waiting, the others wait
     __device__ __forceinline__ void signal(int n) {
-        if (producer) asm volatile("bar.arrive %0, %1;" ::"r"(n), "r"(nt) : "memory");
+        if (producer) {
+            asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(mbar + 8u * (unsigned)(n - 1)) : "memory");
+            if (n == 7) round++;
+        }
     }
     __device__ __forceinline__ void wait(int n) {
-        if (!producer) asm volatile("bar.sync %0, %1;" ::"r"(n), "r"(nt) : "memory");
+        if (!producer) {
+            const unsigned addr = mbar + 8u * (unsigned)(n - 1), ph = round & 1u;
+            unsigned done = 0;
+            for (unsigned spin = 0; !done; spin++) {
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(done) : "r"(addr), "r"(ph) : "memory");
+                if (spin > (1u << 26)) __trap();          // a lost signal must fail loudly, never hang the GPU
+            }
+            if (n == 7) round++;
+        }
     }
     __device__ __forceinline__ void stage_max(const Var2Thread<P, D>&, double a, double b) {
 #pragma unroll
@@ -82,59 +98,78 @@ struct DevVar2Exec {
             a = fmax(a, __shfl_xor_sync(0xffffffffu, a, o));
             b = fmax(b, __shfl_xor_sync(0xffffffffu, b, o));
         }
-        if ((threadIdx.x & 31) == 0) {
-            red[parity * 64 + 2 * (threadIdx.x >> 5)] = a;
-            red[parity * 64 + 2 * (threadIdx.x >> 5) + 1] = b;
+        if ((th.tid & 31) == 0) {
+            red[parity * 16 + 2 * (th.tid >> 5)] = a;
+            red[parity * 16 + 2 * (th.tid >> 5) + 1] = b;
         }
     }
     __device__ __forceinline__ void read_max(double& a, double& b) {
         a = 0.0; b = 0.0;
         for (int w = 0; w < nwarps; w++) {
-            a = fmax(a, red[parity * 64 + 2 * w]);
-            b = fmax(b, red[parity * 64 + 2 * w + 1]);
+            a = fmax(a, red[parity * 16 + 2 * w]);
+            b = fmax(b, red[parity * 16 + 2 * w + 1]);
         }
         parity ^= 1;
     }
     __device__ __forceinline__ long long fetch(unsigned long long* ctr) {
-        unsigned long long* slot = reinterpret_cast<unsigned long long*>(red + 128);
-        __syncthreads();
-        if (threadIdx.x == 0) *slot = atomicAdd(ctr, 1ull);
-        __syncthreads();
+        unsigned long long* slot = reinterpret_cast<unsigned long long*>(red + 32);
+        sync();
+        if (th.tid == 0) *slot = atomicAdd(ctr, 1ull);
+        sync();
         return (long long)*slot;
     }
     __device__ __forceinline__ void add_work(unsigned long long* wc, unsigned long long nf, unsigned long long na) {
-        if (wc && threadIdx.x == 0) { atomicAdd(&wc[0], nf); atomicAdd(&wc[1], na); }
+        if (wc && th.tid == 0) { atomicAdd(&wc[0], nf); atomicAdd(&wc[1], na); }
     }
 };
 
-// MAXR: register cap per thread (__maxnreg__; __launch_bounds__ rounds a 96-thread CTA up to 128 threads when it derives
-// the cap from a CTAs-per-SM target, which would leave 3 x 96 threads only 168 registers each)
-template <int P, int D, int NT, int MAXR>
+// NTG threads per group, G groups per CTA; MAXR: register cap per thread (__maxnreg__: the register file is allocated per
+// CTA in 128-thread units, so G * NTG should be a multiple of 128 and MAXR <= 65536 / (CTA threads x CTAs per SM))
+template <int P, int D, int NTG, int G, int MAXR>
 __global__ void __maxnreg__(MAXR) var2_kernel(const VarArgs a, const Var2Layout L) {
-    extern __shared__ __align__(16) double sm[];
+    extern __shared__ __align__(16) double sm_all[];
+    const int group = (int)threadIdx.x / NTG, gtid = (int)threadIdx.x - group * NTG;
+    double* sm = sm_all + (size_t)group * L.total;
     Var2Thread<P, D> th;
-    var2_assign(th, (int)threadIdx.x, L);
-    DevVar2Exec<P, D> ex{th, sm + L.o_red, 0, NT / 32, NT, (int)(threadIdx.x >> 5) == L.nso_warps};
+    var2_assign(th, gtid, L);
+    unsigned long long* mb = reinterpret_cast<unsigned long long*>(sm + L.o_mbar);
+    if (gtid == 0) {
+#pragma unroll
+        for (int k = 0; k < 7; k++)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 32;" ::"r"(smem_u32(mb + k)) : "memory");
+    }
+    __syncthreads();
+    DevVar2Exec<P, D> ex{th, sm + L.o_red, smem_u32(mb), 0, NTG / 32, NTG, 1 + group, 0u, (gtid >> 5) == L.nso_warps};
     var2_run_items<P, D>(ex, a, L, sm);
 }
 
-template <int P, int D, int NT, int MAXR>
+template <int P, int D, int NTG, int G, int MAXR>
 static cudaError_t launch_var2_one(const VarArgs& a, int nv, int num_sms, cudaStream_t stream) {
-    auto kern = var2_kernel<P, D, NT, MAXR>;
-    const Var2Layout L = var2_layout(P, D, nv, NT);
-    if (var2_min_threads(nv) > NT) return cudaErrorInvalidConfiguration;
-    const size_t smem = sizeof(double) * (size_t)L.total;
+    auto kern = var2_kernel<P, D, NTG, G, MAXR>;
+    const Var2Layout L = var2_layout(P, D, nv, NTG);
+    if (var2_min_threads(nv) > NTG) return cudaErrorInvalidConfiguration;
+    const size_t smem = sizeof(double) * (size_t)L.total * G;
+    if (smem > (size_t)227 * 1024) return cudaErrorInvalidConfiguration;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int occ = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NTG * G, smem);
     if (e != cudaSuccess) return e;
     if (occ < 1) return cudaErrorLaunchOutOfResources;
     long long blocks = (long long)num_sms * occ;
-    if (2 * a.W < blocks) blocks = 2 * a.W;
+    const long long need = (2 * a.W + G - 1) / G;
+    if (need < blocks) blocks = need;
     if (blocks < 1) blocks = 1;
-    kern<<<(unsigned)blocks, NT, smem, stream>>>(a, L);
+    kern<<<(unsigned)blocks, NTG * G, smem, stream>>>(a, L);
     return cudaGetLastError();
+}
+
+// groups of one CTA that fit the SM's shared memory (227 KB), at most gmax
+static int var2_groups(int P, int D, int nv, int ntg, int gmax) {
+    const Var2Layout L = var2_layout(P, D, nv, ntg);
+    const size_t per = sizeof(double) * (size_t)L.total;
+    int g = (int)(((size_t)227 * 1024) / per);
+    return g < 1 ? 0 : (g > gmax ? gmax : g);
 }
 
 // logp = -(chi2b + chi2f), grad = -(db + df), hess symmetric (state.py:285,292-293)
@@ -191,17 +226,18 @@ int var_threads_needed(int P, int nv) {
     return L.need;
 }
 
-// layout: 0 = automatic (set-per-lane kernel where it exists: one or two planets), 1 = thread per (set, planet)
+// layout: 0 = automatic (warp-group kernel where it exists: one or two planets), 1 = thread per (set, planet)
 cudaError_t launch_var(const VarArgs& a, int P, int D, int nv, int layout, int num_sms, cudaStream_t stream) {
-    if (layout == 2 && P == 2 && D == 2 && var2_min_threads(nv) <= 96)       // tuning: 168 registers -> 3 CTAs per SM
-        return launch_var2_one<2, 2, 96, 168>(a, nv, num_sms, stream);
-    if (layout == 0 && var2_supported(P, nv)) {
+    if (layout != 1 && var2_supported(P, nv)) {
         const int nt = var2_min_threads(nv);
-        if (P == 1 && D == 2 && nt <= 64) return launch_var2_one<1, 2, 64, 168>(a, nv, num_sms, stream);
-        if (P == 1 && D == 3 && nt <= 64) return launch_var2_one<1, 3, 64, 224>(a, nv, num_sms, stream);
-        if (P == 2 && D == 2 && nt <= 64) return launch_var2_one<2, 2, 64, 224>(a, nv, num_sms, stream);
-        if (P == 2 && D == 2 && nt <= 96) return launch_var2_one<2, 2, 96, 224>(a, nv, num_sms, stream);
-        if (P == 2 && D == 2 && nt <= 160) return launch_var2_one<2, 2, 160, 200>(a, nv, num_sms, stream);
+        if (P == 2 && D == 2 && nt <= 96) {                       // nv <= 10 (HD155358): 4 x 96 = 384 threads, 168 registers
+            const int g = var2_groups(2, 2, nv, 96, 4);
+            if (layout == 2 || g == 3) return launch_var2_one<2, 2, 96, 3, 224>(a, nv, num_sms, stream);   // tuning / fallback
+            if (g >= 4) return launch_var2_one<2, 2, 96, 4, 168>(a, nv, num_sms, stream);
+        }
+        if (P == 2 && D == 2 && nt <= 160 && var2_groups(2, 2, nv, 160, 2) >= 2) return launch_var2_one<2, 2, 160, 2, 200>(a, nv, num_sms, stream);
+        if (P == 1 && D == 2 && nt <= 64) return launch_var2_one<1, 2, 64, 4, 128>(a, nv, num_sms, stream);
+        if (P == 1 && D == 3 && nt <= 64) return launch_var2_one<1, 3, 64, 4, 168>(a, nv, num_sms, stream);
     }
     const int need = var_threads_needed(P, nv);
     if (P == 1 && D == 2 && need <= 64) return launch_var_one<1, 2, 64, 4>(a, nv, num_sms, stream);
