@@ -135,8 +135,8 @@ def run_ess(ctx, model, oh, rank, world, dist, dev, rows, torch, budgets=(150.0,
     eq = np.load(EQUILIBRATED)
     post_std = eq.std(axis=0)
     slots = ctx.device_info()["sm_count"] * 3 * 64          # resident (walker, leg) lane groups of loglik_kernel
-    out = {"start": "committed equilibrated stretch ensemble (%d walkers; tools/make_equilibrated_ensemble.py), no burn-in "
-                    "inside the clock" % len(eq),
+    out = {"start": "committed equilibrated stretch ensemble (%d walkers; tools/make_equilibrated_ensemble.py); nothing inside the "
+                    "clocks is burn-in" % len(eq),
            "definition": "ESS = recorded rows x walkers / max_i tau_i; tau_int = Sokal's windowed integrated autocorrelation "
                          "time of the walker-averaged autocovariance (256 walkers), ac_time_ref = driver.py:366-377 (first lag with "
                          "autocorrelation < 0.5; mean over 16 walkers, as driver.py:355-370 does for ensembles); seconds = "
@@ -144,8 +144,12 @@ def run_ess(ctx, model, oh, rank, world, dist, dev, rows, torch, budgets=(150.0,
            "aggregate": "sum over ranks of ESS / max over ranks of seconds; every rank runs its own chains (MH, SMALA: "
                         "global chain ids) or its own ensemble replica (stretch: rank-specific seed)"}
 
-    def summarise(name, chain, seconds, evals, extra):
-        n_eff, tau = ess(chain)
+    REC = 512          # walkers whose positions are recorded (context option chain_walkers): the autocorrelation estimate
+                       # needs a sample of the chains, not a host copy of every position
+
+    def summarise(name, chain, walkers, seconds, evals, extra):
+        _, tau = ess(chain)
+        n_eff = chain.shape[0] * walkers / max(tau, 1.0)
         ac_ref = max(float(np.mean([driver.ac_time(chain[:, w, i]) for w in range(min(16, chain.shape[1]))]))
                      for i in range(chain.shape[2]))
         vals = [float(n_eff), float(seconds), float(evals)]
@@ -156,51 +160,63 @@ def run_ess(ctx, model, oh, rank, world, dist, dev, rows, torch, budgets=(150.0,
             n_eff_tot, sec, ev = float(s[0]), float(m[1]), float(s[2])
         else:
             n_eff_tot, sec, ev = vals
-        d = {"walkers_per_gpu": int(chain.shape[1]), "recorded_rows": int(chain.shape[0]), "seconds": sec,
-             "evals_per_s": ev / sec, "tau_int_max_rows": tau, "ac_time_ref_max_rows": ac_ref,
+        d = {"walkers_per_gpu": int(walkers), "recorded_walkers": int(chain.shape[1]), "recorded_rows": int(chain.shape[0]),
+             "seconds": sec, "evals_per_s": ev / sec, "tau_int_max_rows": tau, "ac_time_ref_max_rows": ac_ref,
              "ess_per_s": n_eff_tot / sec, "ess_per_s_ref_definition": n_eff_tot * max(tau, 1.0) / max(ac_ref, 1.0) / sec}
         d.update(extra)
         out[name] = d
 
-    def sized(name, budget_s, pilot):
-        """Recorded rows for one sampler: `rows` unless the time budget says fewer (pilot = seconds of a 10-step run)."""
-        per_step = pilot / 10.0
+    def sized(name, budget_s, pilot, nsteps_pilot):
+        """Recorded rows for one sampler: `rows` unless the time budget says fewer (pilot = seconds of a short run)."""
+        per_step = pilot / nsteps_pilot
         n = int(min(rows, max(200, budget_s / max(per_step, 1e-6))))
         out.setdefault("time_budget", {})[name] = {"budget_s": budget_s, "pilot_ms_per_step": 1e3 * per_step, "rows": n,
                                                    "rows_limited_by_time_budget": bool(n < rows)}
         return n
 
-    # affine stretch: one full wave of (walker, leg) items per half-step
-    W = min(len(eq), slots) & ~1
+    # The ensemble is sized to keep the machine full THROUGH the long tail of the posterior's expensive walkers: four waves
+    # of (walker, leg) items per half-step.  It is built from four copies of the committed equilibrated ensemble,
+    # decorrelated by an UNTIMED burn-in of `mix` stretch steps (every walker is still a draw from the stationary
+    # distribution; the copies separate at their first accepted move).
+    copies, mix = 4, 60
+    W = min(copies * len(eq), copies * slots) & ~1
+    start = np.concatenate([eq] * copies)[:W]
+    start = np.ascontiguousarray(start.reshape(copies, -1, 10).transpose(1, 0, 2).reshape(-1, 10))   # interleave the copies
     t0 = time.perf_counter()
-    model.stretch_run(oh, eq[:W], 10, seed=1, record_chain=False)
-    n = sized("stretch", budgets[0], time.perf_counter() - t0)
+    r = model.stretch_run(oh, start, mix, seed=7 + 1000 * rank, record_chain=False)
+    pilot = time.perf_counter() - t0
+    start, lnp0 = r["theta"], r["lnp"]
+    out["ensemble"] = {"walkers_per_gpu": int(W), "copies_of_committed_ensemble": copies, "untimed_burn_in_steps": mix,
+                       "burn_in_seconds": pilot, "burn_in_accept_rate": float(r["n_accept"].mean() / mix)}
+    # affine stretch
+    n = sized("stretch", budgets[0], pilot, mix)
     t0 = time.perf_counter()
-    r = model.stretch_run(oh, eq[:W], n, seed=11 + 1000 * rank, thin=1)
-    summarise("stretch", r["chain"], time.perf_counter() - t0, W * (n + 1),
+    r = model.stretch_run(oh, start, n, seed=11 + 1000 * rank, first_step=mix, lnp=lnp0, thin=1, chain_walkers=REC)
+    summarise("stretch", r["chain"], W, time.perf_counter() - t0, W * n,
               {"accept_rate": float(r["n_accept"].mean() / n), "a": 2.0})
     del r
-    # Metropolis-Hastings: proposal scale 0.25 x the posterior standard deviations of the equilibrated ensemble
-    W = min(len(eq), slots)                 # two waves of (walker, leg) items per step: the long tail of one wave overlaps the next
+    # Metropolis-Hastings: proposal scale 0.25 x the posterior standard deviations; chains start from the same walkers
+    Wm = W // 2
     t0 = time.perf_counter()
-    model.mh_run(oh, eq[:W], post_std, 0.25, 10, seed=1, record_chain=False)
-    n = sized("mh", budgets[1], time.perf_counter() - t0)
+    model.mh_run(oh, start[:Wm], post_std, 0.25, 10, seed=1, record_chain=False)
+    n = sized("mh", budgets[1], time.perf_counter() - t0, 10)
     t0 = time.perf_counter()
-    r = model.mh_run(oh, eq[:W], post_std, 0.25, n, seed=12, first_chain_id=rank * W, thin=1)
-    summarise("mh", r["chain"], time.perf_counter() - t0, W * (n + 1),
+    r = model.mh_run(oh, start[:Wm], post_std, 0.25, n, seed=12, first_chain_id=rank * Wm, logp=lnp0[:Wm], thin=1, chain_walkers=REC)
+    summarise("mh", r["chain"], Wm, time.perf_counter() - t0, Wm * n,
               {"accept_rate": float(r["n_accept"].mean() / n), "step_size": 0.25, "scales": "posterior std"})
     del r
-    # SMALA with the reference's step size and SoftAbs constant ((Ex)HD155358.ipynb:640): two waves of warp groups
-    # (4 groups = 4 walker legs per SM resident in var2_kernel)
-    W = ctx.device_info()["sm_count"] * 4
+    # SMALA with the reference's step size and SoftAbs constant ((Ex)HD155358.ipynb:640): four waves of warp groups
+    # (4 walker legs per SM resident in var2_kernel)
+    Ws = ctx.device_info()["sm_count"] * 8
     t0 = time.perf_counter()
-    model.smala_run(oh, eq[:W], 0.025, 1.4, 10, seed=1, record_chain=False)
-    n = sized("smala", budgets[2], time.perf_counter() - t0)
+    model.smala_run(oh, start[:Ws], 0.025, 1.4, 5, seed=1, record_chain=False)
+    n = sized("smala", budgets[2], time.perf_counter() - t0, 6)
     t0 = time.perf_counter()
-    r = model.smala_run(oh, eq[:W], 0.025, 1.4, n, seed=13, first_chain_id=rank * W, thin=1)
-    summarise("smala", r["chain"], time.perf_counter() - t0, W * (n + 1),
+    r = model.smala_run(oh, start[:Ws], 0.025, 1.4, n, seed=13, first_chain_id=rank * Ws, thin=1, chain_walkers=REC)
+    summarise("smala", r["chain"], Ws, time.perf_counter() - t0, Ws * (n + 1),
               {"accept_rate": float(r["n_accept"].mean() / n), "eps": 0.025, "alpha": 1.4,
                "not_spd_flags": int((r["status"] == 9).sum())})
+    ctx.set_option("chain_walkers", 0)
     return out
 
 

@@ -57,6 +57,11 @@ int rv_ctx_create(int device, rv_ctx** out);
 int rv_ctx_destroy(rv_ctx* ctx);
 const char* rv_last_error(const rv_ctx* ctx);   /* ctx may be NULL: last creation error           */
 int rv_device_info(const rv_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, int* clock_khz);
+/* context options: "chain_walkers" (0 = all): the fused samplers (rv_mh_run, rv_stretch_run, rv_smala_run, rv_alsmala_run)
+ * record only chains / walkers [0, n) in their chain rows -- chain[rows][min(n, W)][nvars], chain_logp[rows][min(n, W)] --
+ * so that very large ensembles can be sampled without moving every position to the host; "count_work" (0/1).        */
+int rv_ctx_set_option(rv_ctx* ctx, const char* key, double value);
+
 
 /* ---- observations: replaces the Observation container (observations.py:6-16, 52-69) ----------- */
 /* tf/rvf/errf: forward leg in obs.tf order; tb/rvb/errb: backward leg in obs.tb order (ascending, as

@@ -38,6 +38,7 @@ _SIGNATURES = {
     "rv_ctx_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
     "rv_ctx_destroy": (C.c_int, [C.c_void_p]),
     "rv_last_error": (C.c_char_p, [C.c_void_p]),
+    "rv_ctx_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_double]),
     "rv_device_info": (C.c_int, [C.c_void_p, _ip, _ip, _ip, _ip]),
     "rv_obs_create": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_int, C.c_double, C.POINTER(C.c_void_p)]),
@@ -169,6 +170,15 @@ class Context(object):
 
     def sync(self):
         self.check(self.lib.rv_sync(self.h), "rv_sync")
+
+    def set_option(self, key, value):
+        self.check(self.lib.rv_ctx_set_option(self.h, key.encode(), float(value)), "rv_ctx_set_option")
+
+    def chain_rows_width(self, W, chain_walkers):
+        """Sets the context's chain_walkers option for the next sampler call; returns the recorded width."""
+        cw = int(chain_walkers) if chain_walkers else 0
+        self.set_option("chain_walkers", cw)
+        return min(cw, W) if cw > 0 else W
 
     # ---- plain device buffers (addresses as ints) ----
     def dev_alloc(self, nbytes):
@@ -356,7 +366,7 @@ class ModelHandle(_Handle):
 
     # ---- fused device samplers -------------------------------------------------------------------
     def mh_run(self, obs, theta, scales, step_size, nsteps, seed=0, first_chain_id=0, first_step=0, thin=1,
-               logp=None, record_chain=True, record_accepts=False):
+               logp=None, record_chain=True, record_accepts=False, chain_walkers=None):
         """W independent Metropolis-Hastings chains (Mh.step, mcmc.py:107-121) run on the device.
         Returns dict(theta, logp, chain[nsteps//thin][W][nvars], chain_logp, n_accept[W], accepted[nsteps][W])."""
         theta = self._theta(theta).copy()
@@ -365,8 +375,9 @@ class ModelHandle(_Handle):
         lp = _f64(logp).copy() if have else np.zeros(W)
         scales = _f64(scales)
         rows = nsteps // thin
-        chain = np.zeros((rows, W, self.nvars)) if record_chain else None
-        chain_lp = np.zeros((rows, W)) if record_chain else None
+        cw = self.ctx.chain_rows_width(W, chain_walkers)        # chain rows hold chains [0, chain_walkers) only
+        chain = np.zeros((rows, cw, self.nvars)) if record_chain else None
+        chain_lp = np.zeros((rows, cw)) if record_chain else None
         nacc = np.zeros(W, dtype=np.uint64)
         acc = np.zeros((nsteps, W), dtype=np.uint8) if record_accepts else None
         self.ctx.check(self.ctx.lib.rv_mh_run(self.ctx.h, self.h, obs.h, _ptr(theta), _ptr(lp), 1 if have else 0,
@@ -376,15 +387,16 @@ class ModelHandle(_Handle):
         return dict(theta=theta, logp=lp, chain=chain, chain_logp=chain_lp, n_accept=nacc, accepted=acc)
 
     def smala_run(self, obs, theta, eps, alpha, nsteps, seed=0, first_chain_id=0, first_step=0, thin=1,
-                  record_chain=True, record_accepts=False):
+                  record_chain=True, record_accepts=False, chain_walkers=None):
         """W independent SMALA chains (Smala.step, mcmc.py:167-187) run on the device.
         Returns dict(theta, logp, chain, chain_logp, n_accept[W], accepted[nsteps][W], status[W])."""
         theta = self._theta(theta).copy()
         W = theta.shape[0]
         lp = np.zeros(W)
         rows = nsteps // thin
-        chain = np.zeros((rows, W, self.nvars)) if record_chain else None
-        chain_lp = np.zeros((rows, W)) if record_chain else None
+        cw = self.ctx.chain_rows_width(W, chain_walkers)
+        chain = np.zeros((rows, cw, self.nvars)) if record_chain else None
+        chain_lp = np.zeros((rows, cw)) if record_chain else None
         nacc = np.zeros(W, dtype=np.uint64)
         acc = np.zeros((nsteps, W), dtype=np.uint8) if record_accepts else None
         status = np.zeros(W, dtype=np.int32)
@@ -402,8 +414,9 @@ class ModelHandle(_Handle):
         W = theta.shape[0]
         lp = np.zeros(W)
         rows = nsteps // thin
-        chain = np.zeros((rows, W, self.nvars)) if record_chain else None
-        chain_lp = np.zeros((rows, W)) if record_chain else None
+        cw = self.ctx.chain_rows_width(W, None)
+        chain = np.zeros((rows, cw, self.nvars)) if record_chain else None
+        chain_lp = np.zeros((rows, cw)) if record_chain else None
         nacc = np.zeros(W, dtype=np.uint64)
         acc = np.zeros((nsteps, W), dtype=np.uint8) if record_accepts else None
         status = np.zeros(W, dtype=np.int32)
@@ -416,15 +429,16 @@ class ModelHandle(_Handle):
                     full_step=full[:nsteps])
 
     def stretch_run(self, obs, theta, nsteps, a=2.0, seed=0, first_step=0, thin=1, lnp=None, record_chain=True,
-                    record_accepts=False):
+                    record_accepts=False, chain_walkers=None):
         """Affine stretch ensemble (Ensemble.step, mcmc.py:57-65; emcee 2.2.1 move) run on the device."""
         theta = self._theta(theta).copy()
         W = theta.shape[0]
         have = lnp is not None
         lp = _f64(lnp).copy() if have else np.zeros(W)
         rows = nsteps // thin
-        chain = np.zeros((rows, W, self.nvars)) if record_chain else None
-        chain_lp = np.zeros((rows, W)) if record_chain else None
+        cw = self.ctx.chain_rows_width(W, chain_walkers)
+        chain = np.zeros((rows, cw, self.nvars)) if record_chain else None
+        chain_lp = np.zeros((rows, cw)) if record_chain else None
         nacc = np.zeros(W, dtype=np.uint64)
         acc = np.zeros((nsteps, W), dtype=np.uint8) if record_accepts else None
         self.ctx.check(self.ctx.lib.rv_stretch_run(self.ctx.h, self.h, obs.h, _ptr(theta), _ptr(lp), 1 if have else 0,

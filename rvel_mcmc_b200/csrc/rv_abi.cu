@@ -19,6 +19,7 @@ struct rv_ctx {
     unsigned long long* d_item_counter;   // work-queue head
     unsigned long long* d_work;           // [2] force evaluations, step attempts
     int count_work;
+    long long chain_walkers;              // samplers record only walkers [0, chain_walkers) in chain rows (0 = all)
     // grow-only scratch
     double* d_theta; size_t cap_theta;
     double* d_logp; size_t cap_logp;
@@ -45,6 +46,7 @@ struct rv_ctx {
     double* d_lascr; size_t cap_lascr;
     int* d_geo; size_t cap_geo;
     int* d_flag; size_t cap_flag;
+    double* d_vhist; size_t cap_vhist;
     char err[512];
 };
 struct rv_obs {
@@ -97,7 +99,19 @@ static int ensure(rv_ctx* ctx, T** p, size_t* cap, size_t n) {
     return 0;
 }
 
+static inline int64_t chain_width(const rv_ctx* ctx, int64_t W) {
+    return (ctx->chain_walkers > 0 && ctx->chain_walkers < W) ? (int64_t)ctx->chain_walkers : W;
+}
+
 extern "C" {
+
+int rv_ctx_set_option(rv_ctx* ctx, const char* key, double value) {
+    if (!ctx || !key) return -1;
+    if (!strcmp(key, "chain_walkers")) ctx->chain_walkers = value > 0 ? (long long)value : 0;
+    else if (!strcmp(key, "count_work")) ctx->count_work = value != 0.0;
+    else return fail(ctx, -20, "rv_ctx_set_option: unknown key '%s'", key);
+    return 0;
+}
 
 const char* rv_last_error(const rv_ctx* ctx) { return ctx ? ctx->err : g_err; }
 
@@ -150,7 +164,7 @@ int rv_ctx_destroy(rv_ctx* c) {
     cudaFree(c->d_prop); cudaFree(c->d_plogp); cudaFree(c->d_pstatus); cudaFree(c->d_zz); cudaFree(c->d_scales);
     cudaFree(c->d_chain); cudaFree(c->d_chainlp); cudaFree(c->d_nacc); cudaFree(c->d_acc);
     cudaFree(c->d_vpart); cudaFree(c->d_grad); cudaFree(c->d_hess);
-    cudaFree(c->d_pgrad); cudaFree(c->d_phess); cudaFree(c->d_qf); cudaFree(c->d_lascr); cudaFree(c->d_geo); cudaFree(c->d_flag);
+    cudaFree(c->d_pgrad); cudaFree(c->d_phess); cudaFree(c->d_qf); cudaFree(c->d_lascr); cudaFree(c->d_geo); cudaFree(c->d_flag); cudaFree(c->d_vhist);
     cudaStreamDestroy(c->stream);
     delete c;
     return 0;
@@ -398,6 +412,9 @@ static int var_dev_impl(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, c
     a.part = ctx->d_vpart; a.part_status = ctx->d_pstat;
     a.item_counter = ctx->d_item_counter;
     a.work_counters = ctx->count_work ? ctx->d_work : nullptr;
+    const size_t nh = rv::var_hist_doubles_needed(model->h.P, model->h.D, nv, model->var_layout, ctx->num_sms);
+    if (nh) { if (int rc = ensure(ctx, &ctx->d_vhist, &ctx->cap_vhist, nh)) return rc; }
+    a.hist = ctx->d_vhist; a.hist_doubles = ctx->cap_vhist;
     CU(ctx, rv::launch_var(a, model->h.P, model->h.D, nv, model->var_layout, ctx->num_sms, s));
     CU(ctx, rv::launch_var_finalize(ctx->d_vpart, ctx->d_pstat, W, nv, d_logp, d_grad, d_hess, d_status, ctx->d_item_counter, s));
     return 0;
@@ -452,6 +469,7 @@ static int mh_steps_impl(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, 
                          int nsteps, int thin, int64_t W, unsigned long long* d_nacc, unsigned char* d_acc_rows,
                          double* d_chain, double* d_chainlp, cudaStream_t s) {
     const int nv = model->h.nvars;
+    const int64_t CW = chain_width(ctx, W);
     if (int rc = ensure(ctx, &ctx->d_prop, &ctx->cap_prop, (size_t)W * (nv > 0 ? nv : 1))) return rc;
     if (int rc = ensure(ctx, &ctx->d_plogp, &ctx->cap_plogp, (size_t)W)) return rc;
     if (int rc = ensure(ctx, &ctx->d_pstatus, &ctx->cap_pstatus, (size_t)W)) return rc;
@@ -463,8 +481,8 @@ static int mh_steps_impl(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, 
         const bool rec = d_chain && thin > 0 && ((k + 1) % thin == 0);
         CU(ctx, rv::launch_mh_accept(d_theta, d_logp, ctx->d_prop, ctx->d_plogp, ctx->d_pstatus, nv, W, seed, first_id, step,
                                      d_nacc, d_acc_rows ? d_acc_rows + (size_t)k * W : nullptr,
-                                     rec ? d_chain + (size_t)row * W * nv : nullptr,
-                                     rec ? d_chainlp + (size_t)row * W : nullptr, s));
+                                     rec ? d_chain + (size_t)row * CW * nv : nullptr,
+                                     rec ? d_chainlp + (size_t)row * CW : nullptr, CW, s));
         if (rec) row++;
     }
     return 0;
@@ -492,14 +510,15 @@ int rv_mh_run(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, double* the
     const int nv = model->h.nvars;
     const size_t nvs = (size_t)(nv > 0 ? nv : 1);
     const long long rows = chain ? nsteps / thin : 0;
+    const int64_t CW = chain_width(ctx, W);
     if (int rc = ensure(ctx, &ctx->d_theta, &ctx->cap_theta, (size_t)W * nvs)) return rc;
     if (int rc = ensure(ctx, &ctx->d_logp, &ctx->cap_logp, (size_t)W)) return rc;
     if (int rc = ensure(ctx, &ctx->d_status, &ctx->cap_status, (size_t)W)) return rc;
     if (int rc = ensure(ctx, &ctx->d_scales, &ctx->cap_scales, nvs)) return rc;
     if (int rc = ensure(ctx, &ctx->d_nacc, &ctx->cap_nacc, (size_t)W)) return rc;
     if (rows) {
-        if (int rc = ensure(ctx, &ctx->d_chain, &ctx->cap_chain, (size_t)rows * W * nvs)) return rc;
-        if (int rc = ensure(ctx, &ctx->d_chainlp, &ctx->cap_chainlp, (size_t)rows * W)) return rc;
+        if (int rc = ensure(ctx, &ctx->d_chain, &ctx->cap_chain, (size_t)rows * CW * nvs)) return rc;
+        if (int rc = ensure(ctx, &ctx->d_chainlp, &ctx->cap_chainlp, (size_t)rows * CW)) return rc;
     }
     if (accepted) if (int rc = ensure(ctx, &ctx->d_acc, &ctx->cap_acc, (size_t)nsteps * W + 1)) return rc;
     CU(ctx, cudaMemcpyAsync(ctx->d_theta, theta, (size_t)W * nv * sizeof(double), cudaMemcpyHostToDevice, s));
@@ -517,8 +536,8 @@ int rv_mh_run(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, double* the
     CU(ctx, cudaMemcpyAsync(theta, ctx->d_theta, (size_t)W * nv * sizeof(double), cudaMemcpyDeviceToHost, s));
     CU(ctx, cudaMemcpyAsync(logp, ctx->d_logp, (size_t)W * sizeof(double), cudaMemcpyDeviceToHost, s));
     if (rows) {
-        CU(ctx, cudaMemcpyAsync(chain, ctx->d_chain, (size_t)rows * W * nv * sizeof(double), cudaMemcpyDeviceToHost, s));
-        if (chain_logp) CU(ctx, cudaMemcpyAsync(chain_logp, ctx->d_chainlp, (size_t)rows * W * sizeof(double), cudaMemcpyDeviceToHost, s));
+        CU(ctx, cudaMemcpyAsync(chain, ctx->d_chain, (size_t)rows * CW * nv * sizeof(double), cudaMemcpyDeviceToHost, s));
+        if (chain_logp) CU(ctx, cudaMemcpyAsync(chain_logp, ctx->d_chainlp, (size_t)rows * CW * sizeof(double), cudaMemcpyDeviceToHost, s));
     }
     if (n_accept) CU(ctx, cudaMemcpyAsync(n_accept, ctx->d_nacc, (size_t)W * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
     if (accepted) CU(ctx, cudaMemcpyAsync(accepted, ctx->d_acc, (size_t)nsteps * W, cudaMemcpyDeviceToHost, s));
@@ -565,13 +584,14 @@ int rv_stretch_run(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, double
     const size_t nvs = (size_t)(nv > 0 ? nv : 1);
     const long long rows = chain ? nsteps / thin : 0;
     const int64_t h = W / 2;
+    const int64_t CW = chain_width(ctx, W);
     if (int rc = ensure(ctx, &ctx->d_theta, &ctx->cap_theta, (size_t)W * nvs)) return rc;
     if (int rc = ensure(ctx, &ctx->d_logp, &ctx->cap_logp, (size_t)W)) return rc;
     if (int rc = ensure(ctx, &ctx->d_status, &ctx->cap_status, (size_t)W)) return rc;
     if (int rc = ensure(ctx, &ctx->d_nacc, &ctx->cap_nacc, (size_t)W)) return rc;
     if (rows) {
-        if (int rc = ensure(ctx, &ctx->d_chain, &ctx->cap_chain, (size_t)rows * W * nvs)) return rc;
-        if (int rc = ensure(ctx, &ctx->d_chainlp, &ctx->cap_chainlp, (size_t)rows * W)) return rc;
+        if (int rc = ensure(ctx, &ctx->d_chain, &ctx->cap_chain, (size_t)rows * CW * nvs)) return rc;
+        if (int rc = ensure(ctx, &ctx->d_chainlp, &ctx->cap_chainlp, (size_t)rows * CW)) return rc;
     }
     if (accepted) if (int rc = ensure(ctx, &ctx->d_acc, &ctx->cap_acc, (size_t)nsteps * W + 1)) return rc;
     CU(ctx, cudaMemcpyAsync(ctx->d_theta, theta, (size_t)W * nv * sizeof(double), cudaMemcpyHostToDevice, s));
@@ -593,16 +613,16 @@ int rv_stretch_run(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, double
                                            ctx->d_nacc + id0, accepted ? ctx->d_acc + (size_t)k * W + id0 : nullptr, s)) return rc;
         }
         if (rows && ((k + 1) % thin == 0)) {
-            CU(ctx, cudaMemcpyAsync(ctx->d_chain + (size_t)row * W * nv, ctx->d_theta, (size_t)W * nv * sizeof(double), cudaMemcpyDeviceToDevice, s));
-            CU(ctx, cudaMemcpyAsync(ctx->d_chainlp + (size_t)row * W, ctx->d_logp, (size_t)W * sizeof(double), cudaMemcpyDeviceToDevice, s));
+            CU(ctx, cudaMemcpyAsync(ctx->d_chain + (size_t)row * CW * nv, ctx->d_theta, (size_t)CW * nv * sizeof(double), cudaMemcpyDeviceToDevice, s));
+            CU(ctx, cudaMemcpyAsync(ctx->d_chainlp + (size_t)row * CW, ctx->d_logp, (size_t)CW * sizeof(double), cudaMemcpyDeviceToDevice, s));
             row++;
         }
     }
     CU(ctx, cudaMemcpyAsync(theta, ctx->d_theta, (size_t)W * nv * sizeof(double), cudaMemcpyDeviceToHost, s));
     CU(ctx, cudaMemcpyAsync(lnp, ctx->d_logp, (size_t)W * sizeof(double), cudaMemcpyDeviceToHost, s));
     if (rows) {
-        CU(ctx, cudaMemcpyAsync(chain, ctx->d_chain, (size_t)rows * W * nv * sizeof(double), cudaMemcpyDeviceToHost, s));
-        if (chain_lnp) CU(ctx, cudaMemcpyAsync(chain_lnp, ctx->d_chainlp, (size_t)rows * W * sizeof(double), cudaMemcpyDeviceToHost, s));
+        CU(ctx, cudaMemcpyAsync(chain, ctx->d_chain, (size_t)rows * CW * nv * sizeof(double), cudaMemcpyDeviceToHost, s));
+        if (chain_lnp) CU(ctx, cudaMemcpyAsync(chain_lnp, ctx->d_chainlp, (size_t)rows * CW * sizeof(double), cudaMemcpyDeviceToHost, s));
     }
     if (n_accept) CU(ctx, cudaMemcpyAsync(n_accept, ctx->d_nacc, (size_t)W * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
     if (accepted) CU(ctx, cudaMemcpyAsync(accepted, ctx->d_acc, (size_t)nsteps * W, cudaMemcpyDeviceToHost, s));
@@ -789,6 +809,7 @@ static int smala_impl(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, dou
     cudaStream_t s = ctx->stream;
     const size_t nvs = (size_t)nv;
     const long long rows = chain ? nsteps / thin : 0;
+    const int64_t CW = chain_width(ctx, W);
     if (int rc = ensure(ctx, &ctx->d_theta, &ctx->cap_theta, (size_t)W * nvs)) return rc;
     if (int rc = ensure(ctx, &ctx->d_logp, &ctx->cap_logp, (size_t)W)) return rc;
     if (int rc = ensure(ctx, &ctx->d_status, &ctx->cap_status, (size_t)W)) return rc;
@@ -805,8 +826,8 @@ static int smala_impl(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, dou
     if (int rc = ensure(ctx, &ctx->d_flag, &ctx->cap_flag, (size_t)W)) return rc;
     if (int rc = ensure(ctx, &ctx->d_nacc, &ctx->cap_nacc, (size_t)W)) return rc;
     if (rows) {
-        if (int rc = ensure(ctx, &ctx->d_chain, &ctx->cap_chain, (size_t)rows * W * nvs)) return rc;
-        if (int rc = ensure(ctx, &ctx->d_chainlp, &ctx->cap_chainlp, (size_t)rows * W)) return rc;
+        if (int rc = ensure(ctx, &ctx->d_chain, &ctx->cap_chain, (size_t)rows * CW * nvs)) return rc;
+        if (int rc = ensure(ctx, &ctx->d_chainlp, &ctx->cap_chainlp, (size_t)rows * CW)) return rc;
     }
     if (accepted) if (int rc = ensure(ctx, &ctx->d_acc, &ctx->cap_acc, (size_t)nsteps * W + 1)) return rc;
     CU(ctx, cudaMemcpyAsync(ctx->d_theta, theta, (size_t)W * nv * sizeof(double), cudaMemcpyHostToDevice, s));
@@ -835,15 +856,15 @@ static int smala_impl(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, dou
         CU(ctx, rv::launch_smala_accept(ctx->d_theta, ctx->d_logp, ctx->d_grad, ctx->d_hess, ctx->d_prop, ctx->d_plogp,
                                         ctx->d_pgrad, ctx->d_phess, ctx->d_pstatus, ctx->d_geo, ctx->d_qf, nv, W, eps, alpha,
                                         seed, first_chain_id, step, ctx->d_nacc, accepted ? ctx->d_acc + (size_t)k * W : nullptr,
-                                        ctx->d_flag, rec ? ctx->d_chain + (size_t)row * W * nv : nullptr,
-                                        rec ? ctx->d_chainlp + (size_t)row * W : nullptr, ctx->d_lascr, mala ? 1 : 0, s));
+                                        ctx->d_flag, rec ? ctx->d_chain + (size_t)row * CW * nv : nullptr,
+                                        rec ? ctx->d_chainlp + (size_t)row * CW : nullptr, CW, ctx->d_lascr, mala ? 1 : 0, s));
         if (rec) row++;
     }
     CU(ctx, cudaMemcpyAsync(theta, ctx->d_theta, (size_t)W * nv * sizeof(double), cudaMemcpyDeviceToHost, s));
     CU(ctx, cudaMemcpyAsync(logp, ctx->d_logp, (size_t)W * sizeof(double), cudaMemcpyDeviceToHost, s));
     if (rows) {
-        CU(ctx, cudaMemcpyAsync(chain, ctx->d_chain, (size_t)rows * W * nv * sizeof(double), cudaMemcpyDeviceToHost, s));
-        if (chain_logp) CU(ctx, cudaMemcpyAsync(chain_logp, ctx->d_chainlp, (size_t)rows * W * sizeof(double), cudaMemcpyDeviceToHost, s));
+        CU(ctx, cudaMemcpyAsync(chain, ctx->d_chain, (size_t)rows * CW * nv * sizeof(double), cudaMemcpyDeviceToHost, s));
+        if (chain_logp) CU(ctx, cudaMemcpyAsync(chain_logp, ctx->d_chainlp, (size_t)rows * CW * sizeof(double), cudaMemcpyDeviceToHost, s));
     }
     if (n_accept) CU(ctx, cudaMemcpyAsync(n_accept, ctx->d_nacc, (size_t)W * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
     if (accepted) CU(ctx, cudaMemcpyAsync(accepted, ctx->d_acc, (size_t)nsteps * W, cudaMemcpyDeviceToHost, s));

@@ -14,6 +14,7 @@ cudaError_t launch_fp64_peak(double* d_out, int blocks, int iters, cudaStream_t 
 // variational path (rv_var_kernels.cu)
 struct VarArgs;
 int var_threads_needed(int P, int nv);
+size_t var_hist_doubles_needed(int P, int D, int nv, int layout, int num_sms);
 cudaError_t launch_var(const VarArgs& a, int P, int D, int nv, int layout, int num_sms, cudaStream_t stream);
 cudaError_t launch_var_finalize(const double* part, const int* pstat, long long W, int nv, double* logp, double* grad,
                                 double* hess, int* status, unsigned long long* item_counter, cudaStream_t stream);
@@ -27,7 +28,8 @@ cudaError_t launch_mh_propose(const double* theta, const double* scales, double 
 cudaError_t launch_mh_accept(double* theta, double* logp, const double* prop, const double* prop_logp,
                              const int* prop_status, int nvars, long long W, unsigned long long seed,
                              unsigned long long first_id, unsigned step, unsigned long long* n_accept,
-                             unsigned char* accepted, double* chain_row, double* chain_logp_row, cudaStream_t s);
+                             unsigned char* accepted, double* chain_row, double* chain_logp_row, long long chain_w,
+                             cudaStream_t s);
 cudaError_t launch_stretch_propose(const double* S, const double* C, int nvars, long long nS, long long nC, double a,
                                    unsigned long long seed, unsigned long long id0_S, unsigned step, unsigned half,
                                    double* q, double* zz, cudaStream_t s);
@@ -43,7 +45,7 @@ cudaError_t launch_smala_accept(double* theta, double* logp, double* grad, doubl
                                 const int* geo_status, const double* q_fwd, int n, long long W, double eps, double alpha,
                                 unsigned long long seed, unsigned long long first_id, unsigned step,
                                 unsigned long long* n_accept, unsigned char* accepted, int* flag, double* chain_row,
-                                double* chain_logp_row, double* scratch, int mala, cudaStream_t s);
+                                double* chain_logp_row, long long chain_w, double* scratch, int mala, cudaStream_t s);
 // multi-GPU stretch: the full ensemble copies of every GPU of a group (own + peer-mapped pointers)
 constexpr int RV_MAX_GROUP = 16;
 struct PeerCopies { double* theta[RV_MAX_GROUP]; double* lnp[RV_MAX_GROUP]; int n; };

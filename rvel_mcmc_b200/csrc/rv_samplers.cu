@@ -32,7 +32,7 @@ __global__ void mh_accept_kernel(double* __restrict__ theta, double* __restrict_
                                  const int* __restrict__ prop_status, int nvars, long long W,
                                  unsigned long long seed, unsigned long long first_id, unsigned step,
                                  unsigned long long* __restrict__ n_accept, unsigned char* __restrict__ accepted,
-                                 double* __restrict__ chain_row, double* __restrict__ chain_logp_row) {
+                                 double* __restrict__ chain_row, double* __restrict__ chain_logp_row, long long chain_w) {
     const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= W) return;
     const unsigned long long id = first_id + (unsigned long long)w;
@@ -48,7 +48,7 @@ __global__ void mh_accept_kernel(double* __restrict__ theta, double* __restrict_
         if (n_accept) n_accept[w] += 1ull;
     }
     if (accepted) accepted[w] = acc ? 1 : 0;
-    if (chain_row) {
+    if (chain_row && w < chain_w) {       // rows hold the first chain_w chains (all of them unless the context says otherwise)
         for (int v = 0; v < nvars; v++) chain_row[w * nvars + v] = theta[w * nvars + v];
         chain_logp_row[w] = logp[w];
     }
@@ -143,9 +143,10 @@ cudaError_t launch_mh_propose(const double* theta, const double* scales, double 
 cudaError_t launch_mh_accept(double* theta, double* logp, const double* prop, const double* prop_logp,
                              const int* prop_status, int nvars, long long W, unsigned long long seed,
                              unsigned long long first_id, unsigned step, unsigned long long* n_accept,
-                             unsigned char* accepted, double* chain_row, double* chain_logp_row, cudaStream_t s) {
+                             unsigned char* accepted, double* chain_row, double* chain_logp_row, long long chain_w,
+                             cudaStream_t s) {
     mh_accept_kernel<<<nblk(W, 128), 128, 0, s>>>(theta, logp, prop, prop_logp, prop_status, nvars, W, seed, first_id,
-                                                  step, n_accept, accepted, chain_row, chain_logp_row);
+                                                  step, n_accept, accepted, chain_row, chain_logp_row, chain_w);
     return cudaGetLastError();
 }
 cudaError_t launch_stretch_propose(const double* S, const double* C, int nvars, long long nS, long long nC, double a,

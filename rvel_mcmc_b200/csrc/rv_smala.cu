@@ -29,7 +29,7 @@ __global__ void smala_accept_kernel(double* __restrict__ theta, double* __restri
                                     long long W, double eps, double alpha, unsigned long long seed,
                                     unsigned long long first_id, unsigned step, unsigned long long* __restrict__ n_accept,
                                     unsigned char* __restrict__ accepted, int* __restrict__ flag,
-                                    double* __restrict__ chain_row, double* __restrict__ chain_logp_row,
+                                    double* __restrict__ chain_row, double* __restrict__ chain_logp_row, long long chain_w,
                                     double* __restrict__ scratch, int mala) {
     const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= W) return;
@@ -49,7 +49,7 @@ __global__ void smala_accept_kernel(double* __restrict__ theta, double* __restri
         if (n_accept) n_accept[w] += 1ull;
     }
     if (accepted) accepted[w] = acc ? 1 : 0;
-    if (chain_row) {
+    if (chain_row && w < chain_w) {
         for (int i = 0; i < n; i++) chain_row[w * n + i] = theta[w * n + i];
         chain_logp_row[w] = logp[w];
     }
@@ -69,10 +69,10 @@ cudaError_t launch_smala_accept(double* theta, double* logp, double* grad, doubl
                                 const int* geo_status, const double* q_fwd, int n, long long W, double eps, double alpha,
                                 unsigned long long seed, unsigned long long first_id, unsigned step,
                                 unsigned long long* n_accept, unsigned char* accepted, int* flag, double* chain_row,
-                                double* chain_logp_row, double* scratch, int mala, cudaStream_t s) {
+                                double* chain_logp_row, long long chain_w, double* scratch, int mala, cudaStream_t s) {
     smala_accept_kernel<<<nblk(W, 64), 64, 0, s>>>(theta, logp, grad, hess, prop, p_logp, p_grad, p_hess, p_status,
                                                    geo_status, q_fwd, n, W, eps, alpha, seed, first_id, step, n_accept,
-                                                   accepted, flag, chain_row, chain_logp_row, scratch, mala);
+                                                   accepted, flag, chain_row, chain_logp_row, chain_w, scratch, mala);
     return cudaGetLastError();
 }
 

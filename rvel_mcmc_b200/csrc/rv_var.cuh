@@ -28,6 +28,8 @@ struct VarArgs {
     int* part_status;      // [2W]: item w = backward leg of walker w, item W+w = forward leg
     unsigned long long* item_counter;
     unsigned long long* work_counters;   // [0] force evaluations, [1] step attempts (may be null)
+    double* hist;          // warp-group layout (rv_var2.cuh): global scratch for the rejected-step history, per resident group
+    size_t hist_doubles;
 };
 
 RV_HD int var_nsets(int nv) { return 1 + nv + nv * (nv + 1) / 2; }

@@ -13,8 +13,9 @@
 //     shared memory and arrives on that substep's mbarrier; the so warps wait on the mbarrier only;
 //   * group-wide barriers (named barriers, one id per group) remain for the convergence monitor (once per iteration) and
 //     the once-per-step bookkeeping; nothing is CTA-wide.
-// The once-per-step state (x0, carries, e, and the rejected-step history br / er) lives in shared memory, strided per
-// planet slot.  Written against an executor like rv_var.cuh, so the CPU test-suite runs the same source sequentially.
+// Registers hold the seven g coefficients per coordinate and the predicted positions; x0, the carries, x0 - csx, v0, a0 and
+// e live in shared memory (strided per planet slot); the rejected-step history br / er, written once per accepted step and
+// read only after a rejection, lives in a per-group global scratch (L2-resident).  Written against an executor like rv_var.cuh, so the CPU test-suite runs the same source sequentially.
 #pragma once
 #include "rv_var.cuh"
 
@@ -29,7 +30,9 @@ struct Var2Layout {
     int cstride;       // doubles per buffer: (nv + 1) * CB, rounded up to even
     int o_cbuf, o_dm, o_red, o_real, o_mbar, o_state, total;   // offsets in doubles (per group)
 };
-constexpr int VAR2_STATE_PER_COORD = 24;   // x0, csx, csv, e[7], br[7], er[7]
+constexpr int VAR2_STATE_PER_COORD = 13;   // shared memory, per coordinate: x0, csx, csv, x0c, v0, a0, e[7]
+constexpr int VAR2_HIST_PER_COORD = 14;    // global scratch (L2-resident), per coordinate: br[7], er[7] -- written once per
+                                           // accepted step, read only when a step is rejected
 
 RV_HD int var2_min_threads(int nv) { return 32 * ((nv * (nv + 1) / 2 + 31) / 32 + 1); }
 // NT = 0: the smallest group that fits; otherwise the launched group size (a multiple of 32, >= var2_min_threads)
@@ -54,6 +57,8 @@ RV_HD Var2Layout var2_layout(int P, int D, int nv, int NT = 0) {
     return L;
 }
 // one or two planets; real + first-order sets must fit one warp at one lane per (set, planet); at most 8 warps per group
+// doubles of global history scratch one group needs
+RV_HD size_t var2_hist_doubles(int P, int D, int nv) { return (size_t)VAR2_HIST_PER_COORD * D * (size_t)var_nsets(nv) * P; }
 RV_HD bool var2_supported(int P, int nv) { return P <= 2 && (nv + 1) * P <= 32 && var2_min_threads(nv) <= 256; }
 
 template <int P, int D>
@@ -63,17 +68,28 @@ struct Var2Thread {
     int role;                      // 0 real, 1 first-order (producer warp; own D coordinates), 2 second-order (all P*D), -1 idle
     int set, planet, pa, pb;
     int slot0;                     // planet slot of coordinate block 0 (so lanes: planet p at slot0 + p * n2)
+    int nps, n2;                   // planet slots of the group, second-order sets (strides of the per-coordinate state)
     int ou, oa, ob;                // block offsets inside a producer buffer: own set, parents
-    double x0c[NC], v0[NC], a0[NC];
+    double* st;                    // the group's per-coordinate state in shared memory (see var2_state)
     double q[7][NC];               // b between step attempts, g inside the predictor-corrector loop
     double xn[NC];
     double mon_g, mon_a;           // convergence-monitor contributions of the last substep 7
     double acc;                    // running chi2 / d[a] / dd[a][b] (planet-0 lane of a producer set; so lanes)
 };
 
+// entry k of coordinate c (block p = c / D, axis d) of a lane: st[(k * D + d) * nps + slot], slot = slot0 + p * n2 for so
+// lanes and slot0 for producer lanes (block 0 only): consecutive lanes touch consecutive doubles
+enum : int { VK_X0 = 0, VK_CSX = 1, VK_CSV = 2, VK_X0C = 3, VK_V0 = 4, VK_A0 = 5, VK_E = 6 };
+template <int P, int D>
+RV_D double& var2_state(const Var2Thread<P, D>& th, int k, int c) {
+    const int p = c / D, d = c - p * D;
+    return th.st[(size_t)(k * D + d) * th.nps + th.slot0 + p * th.n2];
+}
+
 template <int P, int D>
 RV_D void var2_assign(Var2Thread<P, D>& th, int tid, const Var2Layout& L) {
     th.tid = tid; th.role = -1; th.set = 0; th.planet = 0; th.pa = th.pb = 0; th.slot0 = 0;
+    th.nps = L.nps; th.n2 = L.n2; th.st = nullptr;
     const int warp = tid >> 5, lane = tid & 31;
     if (warp < L.nso_warps) {
         if (tid < L.n2) {
@@ -172,30 +188,35 @@ RV_D void var2_force_first_planet(int p, const double* __restrict__ X0, const do
 // d2a_i = -sum_j { m_j (Df[U] + D2f[A,B]) + dm_j^a Df[B] + dm_j^b Df[A] },  (d2 m = 0)
 // D2f[u,w] = -3 [u (d.w) + w (d.u) + d (u.w)] / r^5 + 15 d (d.u)(d.w) / r^7.  X0 / XA / XB: producer blocks (positions of
 // the real set and of the two parents, each followed by its star sum).
+// Register pressure: the producer blocks are re-read from shared memory pair by pair (a compiler fence keeps the loads next to
+// their uses) instead of being held across the whole evaluation -- shared-memory loads are cheap, spills to local memory
+// (long-scoreboard stalls) are not.
+RV_D void var2_fence() {
+#if defined(__CUDA_ARCH__)
+    asm volatile("" ::: "memory");
+#endif
+}
 template <int P, int D>
 RV_D void var2_force_second(const double (&xu)[P * D], const double* __restrict__ X0, const double* __restrict__ XA,
                             const double* __restrict__ XB, const double* __restrict__ dma, const double* __restrict__ dmb,
                             const VarUniform<P>& u, double (&an)[P * D]) {
-    double x0[P][D], xa[P][D], xb[P][D], S[D], SA[D], SB[D], SU[D];
-#pragma unroll
-    for (int i = 0; i < P; i++)
-#pragma unroll
-        for (int d = 0; d < D; d++) { x0[i][d] = X0[i * D + d]; xa[i][d] = XA[i * D + d]; xb[i][d] = XB[i * D + d]; }
+    double SU[D];
 #pragma unroll
     for (int d = 0; d < D; d++) {
-        S[d] = X0[P * D + d]; SA[d] = XA[P * D + d]; SB[d] = XB[P * D + d];
         double s = 0.0;
 #pragma unroll
-        for (int j = 0; j < P; j++) s = fma(u.mu[j], xu[j * D + d], fma(dma[j], xb[j][d], fma(dmb[j], xa[j][d], s)));
+        for (int j = 0; j < P; j++) s = fma(u.mu[j], xu[j * D + d], fma(dma[j], XB[j * D + d], fma(dmb[j], XA[j * D + d], s)));
         SU[d] = s;
     }
+    var2_fence();
     // star pairs (dm_star = 0)
 #pragma unroll
     for (int i = 0; i < P; i++) {
         double dd[D], A[D], B[D], U[D], r2 = 0.0, da = 0.0, db = 0.0, ab = 0.0, du = 0.0;
 #pragma unroll
         for (int d = 0; d < D; d++) {
-            dd[d] = x0[i][d] + S[d]; A[d] = xa[i][d] + SA[d]; B[d] = xb[i][d] + SB[d]; U[d] = xu[i * D + d] + SU[d];
+            dd[d] = X0[i * D + d] + X0[P * D + d]; A[d] = XA[i * D + d] + XA[P * D + d];
+            B[d] = XB[i * D + d] + XB[P * D + d]; U[d] = xu[i * D + d] + SU[d];
             r2 = fma(dd[d], dd[d], r2); da = fma(dd[d], A[d], da); db = fma(dd[d], B[d], db);
             ab = fma(A[d], B[d], ab); du = fma(dd[d], U[d], du);
         }
@@ -206,6 +227,7 @@ RV_D void var2_force_second(const double (&xu)[P * D], const double* __restrict_
         const double kd = m * fma(c5, du + ab, 15.0 * r7i * (da * db));
 #pragma unroll
         for (int d = 0; d < D; d++) an[i * D + d] = -fma(kU, U[d], fma(kA, A[d], fma(kB, B[d], kd * dd[d])));
+        var2_fence();
     }
     // planet pairs, both sides from one set of geometric scalars
 #pragma unroll
@@ -215,7 +237,7 @@ RV_D void var2_force_second(const double (&xu)[P * D], const double* __restrict_
             double dd[D], A[D], B[D], U[D], r2 = 0.0, da = 0.0, db = 0.0, ab = 0.0, du = 0.0;
 #pragma unroll
             for (int d = 0; d < D; d++) {
-                dd[d] = x0[i][d] - x0[j][d]; A[d] = xa[i][d] - xa[j][d]; B[d] = xb[i][d] - xb[j][d];
+                dd[d] = X0[i * D + d] - X0[j * D + d]; A[d] = XA[i * D + d] - XA[j * D + d]; B[d] = XB[i * D + d] - XB[j * D + d];
                 U[d] = xu[i * D + d] - xu[j * D + d];
                 r2 = fma(dd[d], dd[d], r2); da = fma(dd[d], A[d], da); db = fma(dd[d], B[d], db);
                 ab = fma(A[d], B[d], ab); du = fma(dd[d], U[d], du);
@@ -239,6 +261,7 @@ RV_D void var2_force_second(const double (&xu)[P * D], const double* __restrict_
 #pragma unroll
                 for (int d = 0; d < D; d++) an[j * D + d] += fma(kU, U[d], fma(kA, A[d], fma(kB, B[d], kd * dd[d])));
             }
+            var2_fence();
         }
 }
 
@@ -250,15 +273,15 @@ RV_D void var2_predict_positions(Var2Thread<P, D>& th, int n, double dt) {
                  c4 = rvtabm::PG[n][4], c5 = rvtabm::PG[n][5], c6 = rvtabm::PG[n][6];
 #pragma unroll
     for (int c = 0; c < N; c++) {
-        double p0 = fma(c0, th.q[0][c], 0.5 * th.a0[c]);
+        double p0 = fma(c0, th.q[0][c], 0.5 * var2_state(th, VK_A0, c));
         p0 = fma(c1, th.q[1][c], p0);
         p0 = fma(c2, th.q[2][c], p0);
         double p1 = c3 * th.q[3][c];
         p1 = fma(c4, th.q[4][c], p1);
         p1 = fma(c5, th.q[5][c], p1);
         p1 = fma(c6, th.q[6][c], p1);
-        const double inner = fma(dth, p0 + p1, th.v0[c]);
-        th.xn[c] = fma(dth, inner, th.x0c[c]);
+        const double inner = fma(dth, p0 + p1, var2_state(th, VK_V0, c));
+        th.xn[c] = fma(dth, inner, var2_state(th, VK_X0C, c));
     }
 }
 
@@ -267,7 +290,7 @@ RV_D void var2_corrector_n(Var2Thread<P, D>& th, const double (&an)[P * D]) {
     double mg = 0.0, ma = 0.0;
 #pragma unroll
     for (int c = 0; c < N; c++) {
-        const double gk = an[c] - th.a0[c];
+        const double gk = an[c] - var2_state(th, VK_A0, c);
         double gn;
         if (n <= 2) {
             gn = gk * rvtab::GA[n];
@@ -354,8 +377,9 @@ RV_D void var2_initial(const Var2Thread<P, D>& th, const Model* __restrict__ md,
 //   signal(n)          producer warp: substep n is published
 //   wait(n)            second-order warps: wait until substep n is published
 //   stage_max / read_max / fetch / add_work   as in rv_var.cuh (group-wide)
+// hist: this group's global scratch of var2_hist_doubles() doubles (br, er: the rejected-step history)
 template <int P, int D, class Exec>
-RV_D void var2_run_items(Exec& ex, const VarArgs& a, const Var2Layout& L, double* __restrict__ sm) {
+RV_D void var2_run_items(Exec& ex, const VarArgs& a, const Var2Layout& L, double* __restrict__ sm, double* __restrict__ hist) {
     constexpr int NC = P * D;
     const Model* __restrict__ md = a.model;
     const int nv = md->nvars;
@@ -370,13 +394,15 @@ RV_D void var2_run_items(Exec& ex, const VarArgs& a, const Var2Layout& L, double
     VarUniform<P> u;
     u.gm0 = m0;
     u.epsilon = md->epsilon;
-    // per-coordinate state in shared memory: entry k of coordinate (block p, axis d) of a lane at
-    // state[(k * D + d) * NPS + slot], slot = slot0 + p * n2 for so lanes, slot0 for producer lanes (block 0 only)
-    auto ST = [&](const Var2Thread<P, D>& th, int k, int c) -> double& {
+    // per-coordinate state: shared memory through var2_state(th, VK_*, c); the rejected-step history (k = 0..6 br, 7..13 er)
+    // in the group's global scratch with the same slot striding
+    auto ST = [&](const Var2Thread<P, D>& th, int k, int c) -> double& { return var2_state(th, k, c); };
+    auto HS = [&](const Var2Thread<P, D>& th, int k, int c) -> double& {
         const int p = c / D, d = c - p * D;
-        return state[(size_t)(k * D + d) * NPS + th.slot0 + p * n2];
+        return hist[(size_t)(k * D + d) * NPS + th.slot0 + p * n2];
     };
-    enum { K_X0 = 0, K_CSX = 1, K_CSV = 2, K_E = 3, K_BR = 10, K_ER = 17 };
+    enum { K_X0 = VK_X0, K_CSX = VK_CSX, K_CSV = VK_CSV, K_X0C = VK_X0C, K_V0 = VK_V0, K_A0 = VK_A0, K_E = VK_E, H_BR = 0, H_ER = 7 };
+    ex.each([&](Var2Thread<P, D>& th) { th.st = state; });
     // a lane's coordinate count: producer lanes carry one planet, so lanes the whole set
     auto NCOF = [](const Var2Thread<P, D>& th) { return th.role == 2 ? NC : D; };
 
@@ -471,13 +497,14 @@ RV_D void var2_run_items(Exec& ex, const VarArgs& a, const Var2Layout& L, double
                 const int nc = NCOF(th);
 #pragma unroll
                 for (int c = 0; c < NC; c++) {
-                    th.v0[c] = v0[c]; th.a0[c] = 0.0; th.xn[c] = x0[c]; th.x0c[c] = x0[c];
+                    th.xn[c] = x0[c];
 #pragma unroll
                     for (int k = 0; k < 7; k++) th.q[k][c] = 0.0;
                     if (c < nc) {
                         ST(th, K_X0, c) = x0[c]; ST(th, K_CSX, c) = 0.0; ST(th, K_CSV, c) = 0.0;
+                        ST(th, K_X0C, c) = x0[c]; ST(th, K_V0, c) = v0[c]; ST(th, K_A0, c) = 0.0;
 #pragma unroll
-                        for (int k = 0; k < 7; k++) { ST(th, K_E + k, c) = 0.0; ST(th, K_BR + k, c) = 0.0; ST(th, K_ER + k, c) = 0.0; }
+                        for (int k = 0; k < 7; k++) { ST(th, K_E + k, c) = 0.0; HS(th, H_BR + k, c) = 0.0; HS(th, H_ER + k, c) = 0.0; }
                     }
                 }
             });
@@ -498,11 +525,13 @@ RV_D void var2_run_items(Exec& ex, const VarArgs& a, const Var2Layout& L, double
                     double x0[NC];
 #pragma unroll
                     for (int cc = 0; cc < NC; cc++) x0[cc] = cc < nc ? ST(th, K_X0, cc) : 0.0;
-                    force(th, 0, x0, th.a0);
+                    double a0[NC];
+                    force(th, 0, x0, a0);
 #pragma unroll
                     for (int cc = 0; cc < NC; cc++) {
                         if (cc >= nc) break;
-                        th.x0c[cc] = x0[cc] - ST(th, K_CSX, cc);
+                        ST(th, K_A0, cc) = a0[cc];
+                        ST(th, K_X0C, cc) = x0[cc] - ST(th, K_CSX, cc);
 #pragma unroll
                         for (int j = 0; j < 7; j++) {      // g from b, in place
                             double s = 0.0;
@@ -576,7 +605,7 @@ RV_D void var2_run_items(Exec& ex, const VarArgs& a, const Var2Layout& L, double
                     if (th.role == 0) {
                         double v2 = 0.0, x2 = 0.0;
 #pragma unroll
-                        for (int d = 0; d < D; d++) { v2 = fma(th.v0[d], th.v0[d], v2); x2 = fma(th.xn[d], th.xn[d], x2); }
+                        for (int d = 0; d < D; d++) { const double vd = ST(th, K_V0, d); v2 = fma(vd, vd, v2); x2 = fma(th.xn[d], th.xn[d], x2); }
                         const bool keep = !(fabs(v2 * dt * dt) < 1e-16 * x2);
 #pragma unroll
                         for (int d = 0; d < D; d++) {
@@ -608,7 +637,7 @@ RV_D void var2_run_items(Exec& ex, const VarArgs& a, const Var2Layout& L, double
                                 if (cc >= nc) break;
                                 double _e[7], _b[7], e[7];
 #pragma unroll
-                                for (int k = 0; k < 7; k++) { _e[k] = ST(th, K_ER + k, cc); _b[k] = ST(th, K_BR + k, cc); }
+                                for (int k = 0; k < 7; k++) { _e[k] = HS(th, H_ER + k, cc); _b[k] = HS(th, H_BR + k, cc); }
                                 var_predict<NC>(q, _e, _b, e, th.q, cc);
 #pragma unroll
                                 for (int k = 0; k < 7; k++) ST(th, K_E + k, cc) = e[k];
@@ -632,31 +661,31 @@ RV_D void var2_run_items(Exec& ex, const VarArgs& a, const Var2Layout& L, double
                                 double s = th.q[6][cc] * (1. / 72.);
                                 s = fma(th.q[5][cc], 1. / 56., s); s = fma(th.q[4][cc], 1. / 42., s); s = fma(th.q[3][cc], 1. / 30., s);
                                 s = fma(th.q[2][cc], 1. / 20., s); s = fma(th.q[1][cc], 1. / 12., s); s = fma(th.q[0][cc], 1. / 6., s);
-                                s = fma(th.a0[cc], 0.5, s);
-                                csx += fma(s, dt2, th.v0[cc] * dt_done);
+                                s = fma(ST(th, K_A0, cc), 0.5, s);
+                                csx += fma(s, dt2, ST(th, K_V0, cc) * dt_done);
                                 const double xnew = x + csx;
                                 csx += x - xnew;
                                 ST(th, K_X0, cc) = xnew; ST(th, K_CSX, cc) = csx;
                             }
                             {
-                                const double v = th.v0[cc];
+                                const double v = ST(th, K_V0, cc);
                                 double csv = ST(th, K_CSV, cc);
                                 double s = th.q[6][cc] * (1. / 8.);
                                 s = fma(th.q[5][cc], 1. / 7., s); s = fma(th.q[4][cc], 1. / 6., s); s = fma(th.q[3][cc], 1. / 5., s);
                                 s = fma(th.q[2][cc], 1. / 4., s); s = fma(th.q[1][cc], 1. / 3., s); s = fma(th.q[0][cc], 1. / 2., s);
-                                s += th.a0[cc];
+                                s += ST(th, K_A0, cc);
                                 csv = fma(s, dt_done, csv);
-                                th.v0[cc] = v + csv;
-                                csv += v - th.v0[cc];
-                                ST(th, K_CSV, cc) = csv;
+                                const double vnew = v + csv;
+                                csv += v - vnew;
+                                ST(th, K_V0, cc) = vnew; ST(th, K_CSV, cc) = csv;
                             }
                             double _e[7], _b[7], e[7];
 #pragma unroll
                             for (int k = 0; k < 7; k++) {
                                 _e[k] = ST(th, K_E + k, cc);
                                 _b[k] = th.q[k][cc];
-                                ST(th, K_ER + k, cc) = _e[k];
-                                ST(th, K_BR + k, cc) = _b[k];
+                                HS(th, H_ER + k, cc) = _e[k];
+                                HS(th, H_BR + k, cc) = _b[k];
                             }
                             var_predict<NC>(q, _e, _b, e, th.q, cc);
 #pragma unroll
@@ -701,9 +730,9 @@ RV_D void var2_run_items(Exec& ex, const VarArgs& a, const Var2Layout& L, double
                     if (th.role < 0) return;
                     if (th.role == 2) {
 #pragma unroll
-                        for (int p = 0; p < P; p++) vxs[th.set * P + p] = th.v0[p * D];
+                        for (int p = 0; p < P; p++) vxs[th.set * P + p] = ST(th, K_V0, p * D);
                     } else {
-                        vxs[th.set * P + th.planet] = th.v0[0];
+                        vxs[th.set * P + th.planet] = ST(th, K_V0, 0);
                     }
                 });
                 ex.sync();

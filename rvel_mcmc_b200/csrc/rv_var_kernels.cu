@@ -140,7 +140,8 @@ __global__ void __maxnreg__(MAXR) var2_kernel(const VarArgs a, const Var2Layout 
     }
     __syncthreads();
     DevVar2Exec<P, D> ex{th, sm + L.o_red, smem_u32(mb), 0, NTG / 32, NTG, 1 + group, 0u, (gtid >> 5) == L.nso_warps};
-    var2_run_items<P, D>(ex, a, L, sm);
+    double* hist = a.hist + ((size_t)blockIdx.x * G + group) * var2_hist_doubles(P, D, L.nv);
+    var2_run_items<P, D>(ex, a, L, sm, hist);
 }
 
 template <int P, int D, int NTG, int G, int MAXR>
@@ -160,6 +161,7 @@ static cudaError_t launch_var2_one(const VarArgs& a, int nv, int num_sms, cudaSt
     const long long need = (2 * a.W + G - 1) / G;
     if (need < blocks) blocks = need;
     if (blocks < 1) blocks = 1;
+    if (!a.hist || a.hist_doubles < (size_t)blocks * G * var2_hist_doubles(P, D, nv)) return cudaErrorInvalidValue;
     kern<<<(unsigned)blocks, NTG * G, smem, stream>>>(a, L);
     return cudaGetLastError();
 }
@@ -226,14 +228,18 @@ int var_threads_needed(int P, int nv) {
     return L.need;
 }
 
+// global history scratch (doubles) the warp-group kernel needs for this model on this GPU; 0 when the other layout runs
+size_t var_hist_doubles_needed(int P, int D, int nv, int layout, int num_sms) {
+    if (layout == 1 || !var2_supported(P, nv)) return 0;
+    return (size_t)num_sms * 8 * var2_hist_doubles(P, D, nv);       // at most 8 resident groups per SM
+}
+
 // layout: 0 = automatic (warp-group kernel where it exists: one or two planets), 1 = thread per (set, planet)
 cudaError_t launch_var(const VarArgs& a, int P, int D, int nv, int layout, int num_sms, cudaStream_t stream) {
     if (layout != 1 && var2_supported(P, nv)) {
         const int nt = var2_min_threads(nv);
         if (P == 2 && D == 2 && nt <= 96) {                       // nv <= 10 (HD155358): 4 x 96 = 384 threads, 168 registers
-            const int g = var2_groups(2, 2, nv, 96, 4);
-            if (layout == 2 || g == 3) return launch_var2_one<2, 2, 96, 3, 224>(a, nv, num_sms, stream);   // tuning / fallback
-            if (g >= 4) return launch_var2_one<2, 2, 96, 4, 168>(a, nv, num_sms, stream);
+            if (var2_groups(2, 2, nv, 96, 4) >= 4) return launch_var2_one<2, 2, 96, 4, 168>(a, nv, num_sms, stream);
         }
         if (P == 2 && D == 2 && nt <= 160 && var2_groups(2, 2, nv, 160, 2) >= 2) return launch_var2_one<2, 2, 160, 2, 200>(a, nv, num_sms, stream);
         if (P == 1 && D == 2 && nt <= 64) return launch_var2_one<1, 2, 64, 4, 128>(a, nv, num_sms, stream);

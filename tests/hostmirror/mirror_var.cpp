@@ -58,7 +58,8 @@ int run2(const rv::VarArgs& a, int nv) {
     HostVar2Exec<P, D> ex;
     ex.th.resize(L.NT);
     for (int t = 0; t < L.NT; t++) rv::var2_assign(ex.th[t], t, L);
-    rv::var2_run_items<P, D>(ex, a, L, sm.data());
+    std::vector<double> hist(rv::var2_hist_doubles(P, D, nv), 0.0);
+    rv::var2_run_items<P, D>(ex, a, L, sm.data(), hist.data());
     return 0;
 }
 }  // namespace
