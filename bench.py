@@ -205,9 +205,9 @@ def run_ess(ctx, model, oh, rank, world, dist, dev, rows, torch, budgets=(150.0,
     summarise("mh", r["chain"], Wm, time.perf_counter() - t0, Wm * n,
               {"accept_rate": float(r["n_accept"].mean() / n), "step_size": 0.25, "scales": "posterior std"})
     del r
-    # SMALA with the reference's step size and SoftAbs constant ((Ex)HD155358.ipynb:640): four waves of warp groups
+    # SMALA with the reference's step size and SoftAbs constant ((Ex)HD155358.ipynb:640): two waves of warp groups
     # (4 walker legs per SM resident in var2_kernel)
-    Ws = ctx.device_info()["sm_count"] * 8
+    Ws = ctx.device_info()["sm_count"] * 4
     t0 = time.perf_counter()
     model.smala_run(oh, start[:Ws], 0.025, 1.4, 5, seed=1, record_chain=False)
     n = sized("smala", budgets[2], time.perf_counter() - t0, 6)

@@ -28,7 +28,7 @@ struct Var2Layout {
     int nps;           // planet slots: nsets * P (so lane t, planet p -> p * n2 + t; producer lane (s, p) -> n2 * P + s * P + p)
     int CB;            // doubles per producer-set block in a buffer: P*D positions + D star sum
     int cstride;       // doubles per buffer: (nv + 1) * CB, rounded up to even
-    int o_cbuf, o_dm, o_red, o_real, o_mbar, o_state, total;   // offsets in doubles (per group)
+    int o_cbuf, o_dm, o_red, o_real, o_mbar, o_uni, o_state, total;   // offsets in doubles (per group)
 };
 constexpr int VAR2_STATE_PER_COORD = 13;   // shared memory, per coordinate: x0, csx, csv, x0c, v0, a0, e[7]
 constexpr int VAR2_HIST_PER_COORD = 14;    // global scratch (L2-resident), per coordinate: br[7], er[7] -- written once per
@@ -51,6 +51,7 @@ RV_HD Var2Layout var2_layout(int P, int D, int nv, int NT = 0) {
     L.o_red = o; o += 2 * 2 * 8 + 2;        // ping-pong group maxima (up to 8 warps) + the item broadcast slot
     L.o_real = o; o += P * D; if (o & 1) o++;      // the real lanes' last force (step-size control)
     L.o_mbar = o; o += 8;                   // seven substep mbarriers (8 bytes each)
+    L.o_uni = o; o += 8;                    // the walker's masses (VarUniform): read from shared memory where they are used
     L.o_state = o; o += VAR2_STATE_PER_COORD * D * L.nps;
     if (o & 1) o++;
     L.total = o;
@@ -108,46 +109,17 @@ RV_D void var2_assign(Var2Thread<P, D>& th, int tid, const Var2Layout& L) {
     th.oa = (1 + th.pa) * L.CB; th.ob = (1 + th.pb) * L.CB;
 }
 
-// ---- forces on ONE planet (producer lanes) -------------------------------------------------------------------------
-// real set: a_p = -m0 f(x_p + S) - sum_{j != p} m_j f(x_p - x_j), f(d) = d / r^3, S = sum mu_j x_j (= -r_star)
+// ---- force on ONE planet of a producer set (real or first-order), one code path for both -------------------------------
+// real set:         a_p  = -m0 f(x_p + S) - sum_{j != p} m_j f(x_p - x_j),  f(d) = d / r^3,  S = sum mu_j x_j (= -r_star)
+// first-order set:  da_p = -sum_j { m_j Df[U_pj] + dm_j f(d_pj) },  Df[u] = u / r^3 - 3 d (d.u) / r^5; star terms with
+//                   d = x0_p + S, u = xu_p + SU, dm_star = 0
+// Both need the same pair geometry (d, 1/r^3) of the REAL positions, so every producer lane evaluates both and keeps the one
+// its set needs: the real lanes do not diverge from the first-order lanes of their warp (for them XU = X0, result unused).
 template <int P, int D>
-RV_D void var2_force_real_planet(int p, const double* __restrict__ X0, const double (&S)[D], const VarUniform<P>& u,
-                                 double (&an)[P * D]) {
-    double xp[D];
-#pragma unroll
-    for (int d = 0; d < D; d++) {
-        xp[d] = X0[d];
-#pragma unroll
-        for (int k = 1; k < P; k++) xp[d] = (p == k) ? X0[k * D + d] : xp[d];
-    }
-    double ds[D], r2 = 0.0;
-#pragma unroll
-    for (int d = 0; d < D; d++) { ds[d] = xp[d] + S[d]; r2 = fma(ds[d], ds[d], r2); }
-    double y = rinv1(r2);
-    double k = -u.gm0 * (y * y * y);
-#pragma unroll
-    for (int d = 0; d < D; d++) an[d] = k * ds[d];
-#pragma unroll
-    for (int j = 0; j < P; j++) {
-        if (P == 1) break;
-        double dp[D];
-        r2 = 0.0;
-#pragma unroll
-        for (int d = 0; d < D; d++) { dp[d] = xp[d] - X0[j * D + d]; r2 = fma(dp[d], dp[d], r2); }
-        y = rinv1(j == p ? 1.0 : r2);
-        k = (j == p) ? 0.0 : -u.gm[j] * (y * y * y);
-#pragma unroll
-        for (int d = 0; d < D; d++) an[d] = fma(k, dp[d], an[d]);
-    }
-}
-
-// first-order set U with mass variations dmu[j] (= d mu_j):  da_p = -sum_j { m_j Df[U_pj] + dm_j f(d_pj) },
-// Df[u] = u / r^3 - 3 d (d.u) / r^5; star terms with d = x0_p + S, u = xu_p + SU, dm_star = 0
-template <int P, int D>
-RV_D void var2_force_first_planet(int p, const double* __restrict__ X0, const double* __restrict__ XU, const double (&S)[D],
-                                  const double (&SU)[D], const double* __restrict__ dmu, const VarUniform<P>& u,
-                                  double (&an)[P * D]) {
-    double x0p[D], xup[D];
+RV_D void var2_force_producer_planet(bool real, int p, const double* __restrict__ X0, const double* __restrict__ XU,
+                                     const double (&S)[D], const double (&SU)[D], const double* __restrict__ dmu,
+                                     const VarUniform<P>& u, double (&an)[P * D]) {
+    double x0p[D], xup[D], ar[D], af[D];
 #pragma unroll
     for (int d = 0; d < D; d++) {
         x0p[d] = X0[d]; xup[d] = XU[d];
@@ -164,7 +136,7 @@ RV_D void var2_force_first_planet(int p, const double* __restrict__ X0, const do
         const double y = rinv1(r2), y2 = y * y, r3i = y * y2, r5i = r3i * y2;
         const double kU = -u.gm0 * r3i, kd = u.gm0 * 3.0 * r5i * du;
 #pragma unroll
-        for (int d = 0; d < D; d++) an[d] = fma(kU, U[d], kd * dd[d]);
+        for (int d = 0; d < D; d++) { ar[d] = kU * dd[d]; af[d] = fma(kU, U[d], kd * dd[d]); }
     }
 #pragma unroll
     for (int j = 0; j < P; j++) {
@@ -180,8 +152,10 @@ RV_D void var2_force_first_planet(int p, const double* __restrict__ X0, const do
         const double kU = mj * r3i;
         const double kd = fma(mj * (-3.0 * r5i), du, dmj * r3i);
 #pragma unroll
-        for (int d = 0; d < D; d++) an[d] -= fma(kU, U[d], kd * dd[d]);
+        for (int d = 0; d < D; d++) { ar[d] = fma(-kU, dd[d], ar[d]); af[d] -= fma(kU, U[d], kd * dd[d]); }
     }
+#pragma unroll
+    for (int d = 0; d < D; d++) an[d] = real ? ar[d] : af[d];
 }
 
 // ---- force on a whole second-order set (so lanes) ------------------------------------------------------------------
@@ -391,9 +365,11 @@ RV_D void var2_run_items(Exec& ex, const VarArgs& a, const Var2Layout& L, double
     double* const state = sm + L.o_state;
     const double m0 = md->m_star;
     const long long n_items = 2 * a.W;
-    VarUniform<P> u;
-    u.gm0 = m0;
-    u.epsilon = md->epsilon;
+    // group-uniform masses live in shared memory (every thread writes the same values): values read through this
+    // reference are re-loaded after each barrier instead of occupying registers across the whole integration
+    static_assert(sizeof(VarUniform<P>) <= 8 * sizeof(double), "VarUniform must fit its shared-memory slot");
+    VarUniform<P>& u = *reinterpret_cast<VarUniform<P>*>(sm + L.o_uni);
+    const double epsilon = md->epsilon;
     // per-coordinate state: shared memory through var2_state(th, VK_*, c); the rejected-step history (k = 0..6 br, 7..13 er)
     // in the group's global scratch with the same slot striding
     auto ST = [&](const Var2Thread<P, D>& th, int k, int c) -> double& { return var2_state(th, k, c); };
@@ -431,8 +407,6 @@ RV_D void var2_run_items(Exec& ex, const VarArgs& a, const Var2Layout& L, double
                 el[i][k] = (s >= 0) ? a.theta[wi * nv + s] : md->fixed[i * NELEM + k];
             }
             bad = bad || prior_hard(el[i]);
-            u.gm[i] = el[i][EL_M];
-            u.mu[i] = el[i][EL_M] / m0;
         }
         int final_status = -1;
         unsigned long long n_force = 0, n_attempt = 0;
@@ -444,7 +418,11 @@ RV_D void var2_run_items(Exec& ex, const VarArgs& a, const Var2Layout& L, double
                 if (rh > hill) hill = rh;
             }
             const double emd = md->hill_factor * hill;
-            u.min2 = emd * emd;
+            ex.sync();                                  // nobody still reads the previous item's masses
+#pragma unroll
+            for (int i = 0; i < P; i++) { u.gm[i] = el[i][EL_M]; u.mu[i] = el[i][EL_M] / m0; }
+            u.gm0 = m0; u.epsilon = epsilon; u.min2 = emd * emd;
+            ex.sync();
 
             // Producer lanes publish their planet's position into buffer b (x0 or the predicted xn), and -- after a
             // producer-warp sync -- the planet-0 lane of each set adds the set's star sum:
@@ -484,8 +462,7 @@ RV_D void var2_run_items(Exec& ex, const VarArgs& a, const Var2Layout& L, double
                     double S[D], SU[D];
 #pragma unroll
                     for (int d = 0; d < D; d++) { S[d] = Xr[NC + d]; SU[d] = Xr[th.ou + NC + d]; }
-                    if (th.role == 1) var2_force_first_planet<P, D>(th.planet, Xr, Xr + th.ou, S, SU, dm + th.pa * P, u, an);
-                    else var2_force_real_planet<P, D>(th.planet, Xr, S, u, an);
+                    var2_force_producer_planet<P, D>(th.role == 0, th.planet, Xr, Xr + th.ou, S, SU, dm + th.pa * P, u, an);
                 }
             };
 
@@ -622,7 +599,7 @@ RV_D void var2_run_items(Exec& ex, const VarArgs& a, const Var2Layout& L, double
                 const double err = maxb6 / maxak;
                 const double dt_done = dt;
                 double dt_new;
-                if (is_normal(err)) dt_new = inv_root7(err / u.epsilon) * dt_done;
+                if (is_normal(err)) dt_new = inv_root7(err / epsilon) * dt_done;
                 else dt_new = dt_done * 4.0;
                 int result = 0;
                 if (fabs(dt_new) < 0.25 * fabs(dt_done)) {
