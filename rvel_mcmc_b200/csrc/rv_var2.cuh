@@ -31,6 +31,10 @@ struct Var2Layout {
     int o_cbuf, o_dm, o_red, o_real, o_mbar, o_uni, o_state, total;   // offsets in doubles (per group)
 };
 constexpr int VAR2_STATE_PER_COORD = 13;   // shared memory, per coordinate: x0, csx, csv, x0c, v0, a0, e[7]
+// Each planet slot owns one contiguous block [entry k][axis d] of an ODD number of doubles: a lane reaches every entry from
+// one base pointer with compile-time offsets (no address arithmetic in the substep loop), and consecutive lanes' 8-byte
+// accesses fall into distinct bank pairs.
+RV_HD int var2_slot_stride(int D) { return (VAR2_STATE_PER_COORD * D) | 1; }
 constexpr int VAR2_HIST_PER_COORD = 14;    // global scratch (L2-resident), per coordinate: br[7], er[7] -- written once per
                                            // accepted step, read only when a step is rejected
 
@@ -52,7 +56,7 @@ RV_HD Var2Layout var2_layout(int P, int D, int nv, int NT = 0) {
     L.o_real = o; o += P * D; if (o & 1) o++;      // the real lanes' last force (step-size control)
     L.o_mbar = o; o += 8;                   // seven substep mbarriers (8 bytes each)
     L.o_uni = o; o += 8;                    // the walker's masses (VarUniform): read from shared memory where they are used
-    L.o_state = o; o += VAR2_STATE_PER_COORD * D * L.nps;
+    L.o_state = o; o += var2_slot_stride(D) * L.nps;
     if (o & 1) o++;
     L.total = o;
     return L;
@@ -78,13 +82,14 @@ struct Var2Thread {
     double acc;                    // running chi2 / d[a] / dd[a][b] (planet-0 lane of a producer set; so lanes)
 };
 
-// entry k of coordinate c (block p = c / D, axis d) of a lane: st[(k * D + d) * nps + slot], slot = slot0 + p * n2 for so
-// lanes and slot0 for producer lanes (block 0 only): consecutive lanes touch consecutive doubles
+// entry k of coordinate c (block p = c / D, axis d) of a lane: st[slot * stride + k * D + d], slot = slot0 + p * n2 for so
+// lanes and slot0 for producer lanes (block 0 only)
 enum : int { VK_X0 = 0, VK_CSX = 1, VK_CSV = 2, VK_X0C = 3, VK_V0 = 4, VK_A0 = 5, VK_E = 6 };
 template <int P, int D>
 RV_D double& var2_state(const Var2Thread<P, D>& th, int k, int c) {
+    constexpr int STRIDE = (VAR2_STATE_PER_COORD * D) | 1;
     const int p = c / D, d = c - p * D;
-    return th.st[(size_t)(k * D + d) * th.nps + th.slot0 + p * th.n2];
+    return th.st[(th.slot0 + p * th.n2) * STRIDE + k * D + d];
 }
 
 template <int P, int D>
@@ -375,7 +380,7 @@ RV_D void var2_run_items(Exec& ex, const VarArgs& a, const Var2Layout& L, double
     auto ST = [&](const Var2Thread<P, D>& th, int k, int c) -> double& { return var2_state(th, k, c); };
     auto HS = [&](const Var2Thread<P, D>& th, int k, int c) -> double& {
         const int p = c / D, d = c - p * D;
-        return hist[(size_t)(k * D + d) * NPS + th.slot0 + p * n2];
+        return hist[(size_t)(th.slot0 + p * n2) * (VAR2_HIST_PER_COORD * D) + k * D + d];
     };
     enum { K_X0 = VK_X0, K_CSX = VK_CSX, K_CSV = VK_CSV, K_X0C = VK_X0C, K_V0 = VK_V0, K_A0 = VK_A0, K_E = VK_E, H_BR = 0, H_ER = 7 };
     ex.each([&](Var2Thread<P, D>& th) { th.st = state; });

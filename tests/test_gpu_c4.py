@@ -71,6 +71,8 @@ def test_c4_mh_identical_decisions(ctx):
     assert sg[0] == 0
     scales = 1.0 / np.sqrt(-np.diag(hg[0]))
     r = PH.mh_horizon(ctx, "c4", 32, 1000, scales, 0.6, seed=7)
+    from test_gpu_parity_horizon import _record
+    _record(r)
     assert r["first_divergent_step"] is None and r["mismatched_decisions"] == 0, r
     assert 0.15 < r["accept_rate"] < 0.5, r
     assert r["max_abs_theta_diff"] < 1e-9 and r["max_abs_logp_diff"] < 1e-6

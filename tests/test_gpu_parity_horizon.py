@@ -21,7 +21,19 @@ def ctx():
     c.close()
 
 
+def _record(r):
+    """With RV_PARITY_REPORT=<file> every comparison appends its summary (first diverging step, mismatches, timings) as one
+    JSON line -- the committed copy is profiles/r02_parity_horizon.jsonl."""
+    import json
+    import os
+    path = os.environ.get("RV_PARITY_REPORT")
+    if path:
+        with open(path, "a") as f:
+            f.write(json.dumps(r) + "\n")
+
+
 def _check(r, theta_tol=1e-9):
+    _record(r)
     assert r["first_divergent_step"] is None and r["mismatched_decisions"] == 0, r
     assert 0.05 < r["accept_rate"] < 0.95, r
     assert r["max_abs_theta_diff"] <= theta_tol, r
