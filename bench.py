@@ -169,7 +169,7 @@ def run_ess(ctx, model, oh, rank, world, dist, dev, rows, torch, budgets=(150.0,
     def sized(name, budget_s, pilot, nsteps_pilot):
         """Recorded rows for one sampler: `rows` unless the time budget says fewer (pilot = seconds of a short run)."""
         per_step = pilot / nsteps_pilot
-        n = int(min(rows, max(200, budget_s / max(per_step, 1e-6))))
+        n = int(min(rows, max(50, budget_s / max(per_step, 1e-6))))
         out.setdefault("time_budget", {})[name] = {"budget_s": budget_s, "pilot_ms_per_step": 1e3 * per_step, "rows": n,
                                                    "rows_limited_by_time_budget": bool(n < rows)}
         return n
@@ -383,7 +383,8 @@ def main():
         run_reference(args)
         return
     if args.quick:
-        args.ess_rows = min(args.ess_rows, 200)
+        args.ess_rows = min(args.ess_rows, 100)
+        args.ess_budget = "5,3,5"
         args.no_cpu_baseline = True
 
     import torch

@@ -39,7 +39,8 @@ def test_reference_arm_other_ranks_exit_quietly():
 
 @pytest.mark.gpu
 def test_gpu_arm_line():
-    d = _one_line(["--steps", "3", "--warmup", "3", "--walkers", "8192", "--cpu-sample", "256"], 900)
+    d = _one_line(["--steps", "3", "--warmup", "3", "--walkers", "8192", "--cpu-sample", "256", "--ess-rows", "60",
+                   "--ess-budget", "4,3,4"], 900)
     assert COMMON <= set(d) and "impl" not in d
     assert d["n_gpus"] == 1 and d["steps"] == 3 and d["warmup"] == 3 and d["scaling"] == "weak" and d["dtype"] == "f64"
     assert d["gpu_launches"] == 6 and d["value"] > 1e5
@@ -49,3 +50,8 @@ def test_gpu_arm_line():
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["parity_status_equal"] and cb["parity_max_abs_logp_diff"] < 1e-6
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    # side blocks: ESS/s of the three samplers from the equilibrated ensemble, the variational kernel, profile-sourced figures
+    for k in ("stretch", "mh", "smala"):
+        assert d["ess"][k]["ess_per_s"] > 0 and d["ess"][k]["recorded_rows"] >= 50 and 0.05 < d["ess"][k]["accept_rate"] < 0.95
+    assert d["var"]["value"] > 1e3 and 0 < d["var"]["roofline"]["frac"] < 1.2
+    assert rf["from_profile"]["file"] == "profiles/roofline_inputs.json" and "source" in rf["from_profile"]["loglik_kernel"]
