@@ -40,15 +40,16 @@ def hist(ins, title):
 def main():
     ll = sass("_ZN2rv13loglik_kernelILi2ELi2ELi1ELi128ELi3ELi0EEEvNS_10LoglikArgsE")
     idx = [i for i, (op, l) in enumerate(ll) if op == "MUFU" and "RSQ64H" in l]
-    # the unrolled predictor-corrector loop holds 14 consecutive rsqrt seeds (7 substeps x (star, planet pair)) with equal spacing
+    # the unrolled predictor-corrector loop holds 14 consecutive rsqrt seeds (7 substeps x (star pair, planet pair)): take the
+    # tightest window of 15 seeds -- from the first seed of substep 1 to the first seed of the next code region
     best = None
     for k in range(len(idx) - 14):
-        gaps = [idx[k + j + 2] - idx[k + j] for j in range(0, 12, 2)]
-        if max(gaps) - min(gaps) < 60 and (best is None or k > best):
-            best = k
+        span = idx[k + 14] - idx[k]
+        if best is None or span < best[0]:
+            best = (span, k)
     if best is not None:
-        a, b = idx[best], idx[best + 14]
-        hist(ll[a:b], "loglik_kernel<2,2,1,128,3,0>  one predictor-corrector iteration (7 substeps)")
+        a, b = idx[best[1]], idx[best[1] + 14]
+        hist(ll[a:b], "loglik_kernel<2,2,1,128,3,0>  seven Gauss-Radau substeps (one predictor-corrector iteration)")
         print("   per substep: %.1f instructions" % ((b - a) / 7.0))
     hist(ll, "loglik_kernel<2,2,1,128,3,0>  whole kernel (static)")
     v2 = sass("_ZN2rv11var2_kernelILi2ELi2ELi96ELi4ELi168EEEvNS_7VarArgsENS_10Var2LayoutE")
