@@ -211,3 +211,34 @@ def test_observation_edits_reach_the_device():
     h2 = obs._handle(c2)
     c2.close()
     assert h2.h is None
+
+
+def test_chain_walkers_records_a_prefix_of_the_ensemble():
+    """Context option chain_walkers: chain rows hold walkers [0, n) only; everything else (final state, acceptance counts,
+    the recorded values themselves) is unchanged."""
+    from rvel_mcmc_b200 import _abi
+    ctx = _abi.Context(0)
+    try:
+        obs = T.load_vels("HD155358.vels")
+        oh = _abi.ObsHandle(ctx, obs.tf, obs.rvf, obs.errorf, obs.tb, obs.rvb, obs.errorb, obs.Npoints)
+        m = _abi.ModelHandle(ctx, np.zeros((2, 7)), T.FP10, T.FE10, 2.0)
+        theta = T.gaussian_ball(T.HD_SOL, T.HD_SCALE_VEC, 64, 9)
+        full = m.stretch_run(oh, theta, 6, seed=3, thin=2)
+        part = m.stretch_run(oh, theta, 6, seed=3, thin=2, chain_walkers=10)
+        assert part["chain"].shape == (3, 10, 10) and part["chain_lnp"].shape == (3, 10)
+        assert np.array_equal(part["chain"], full["chain"][:, :10]) and np.array_equal(part["chain_lnp"], full["chain_lnp"][:, :10])
+        assert np.array_equal(part["theta"], full["theta"]) and np.array_equal(part["n_accept"], full["n_accept"])
+        sc = np.array(T.HD_SCALE_VEC)
+        fm = m.mh_run(oh, theta, sc, 0.1, 5, seed=4)
+        pm = m.mh_run(oh, theta, sc, 0.1, 5, seed=4, chain_walkers=7)
+        assert pm["chain"].shape == (5, 7, 10) and np.array_equal(pm["chain"], fm["chain"][:, :7])
+        assert np.array_equal(pm["chain_logp"], fm["chain_logp"][:, :7]) and np.array_equal(pm["theta"], fm["theta"])
+        fs = m.smala_run(oh, theta[:16], 0.025, 1.4, 3, seed=5)
+        ps = m.smala_run(oh, theta[:16], 0.025, 1.4, 3, seed=5, chain_walkers=4)
+        assert ps["chain"].shape == (3, 4, 10) and np.array_equal(ps["chain"], fs["chain"][:, :4])
+        assert np.array_equal(ps["theta"], fs["theta"])
+        # the option is per call: the next call without it records every walker again
+        again = m.stretch_run(oh, theta, 2, seed=3)
+        assert again["chain"].shape == (2, 64, 10)
+    finally:
+        ctx.close()
