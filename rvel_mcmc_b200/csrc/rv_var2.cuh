@@ -78,7 +78,6 @@ struct Var2Thread {
     double* st;                    // the group's per-coordinate state in shared memory (see var2_state)
     double q[7][NC];               // b between step attempts, g inside the predictor-corrector loop
     double xn[NC];
-    double pp[NC], gnew[NC];       // software-pipelined predictor: partial sum without the g updated last, and that g
     double mon_g, mon_a;           // convergence-monitor contributions of the last substep 7
     double acc;                    // running chi2 / d[a] / dd[a][b] (planet-0 lane of a producer set; so lanes)
 };
@@ -246,76 +245,65 @@ RV_D void var2_force_second(const double (&xu)[P * D], const double* __restrict_
 }
 
 // ---- predictor / corrector over the first N coordinates of a lane ------------------------------------------------------
-// Software-pipelined and table-driven (the substep index n is a runtime value; one code path for all seven substeps):
-//   predictor   x_n = x0c + dth (v0 + dth (pp + PGL[n] gnew)),  pp = a0/2 + sum_k PGX[n][k] g_k  -- every term but the one
-//               of the g coefficient the previous substep updated (gnew), summed while that substep's force was in flight;
-//   corrector   g_{n-1} = fma(a_n, GA[n], sc),  sc = -a0 GA[n] - sum_i g_i GB[n][i]  (GB[n][i] = 0 for i >= n - 1), formed
-//               next to the force evaluation, so the new g is ONE operation after the force.
 template <int N, int P, int D>
 RV_D void var2_predict_positions(Var2Thread<P, D>& th, int n, double dt) {
     const double dth = dt * rvtabm::H[n];
-    const double cl = rvtabm::PGL[n];
+    const double c0 = rvtabm::PG[n][0], c1 = rvtabm::PG[n][1], c2 = rvtabm::PG[n][2], c3 = rvtabm::PG[n][3],
+                 c4 = rvtabm::PG[n][4], c5 = rvtabm::PG[n][5], c6 = rvtabm::PG[n][6];
 #pragma unroll
     for (int c = 0; c < N; c++) {
-        const double p = fma(cl, th.gnew[c], th.pp[c]);
-        const double inner = fma(dth, p, var2_state(th, VK_V0, c));
+        double p0 = fma(c0, th.q[0][c], 0.5 * var2_state(th, VK_A0, c));
+        p0 = fma(c1, th.q[1][c], p0);
+        p0 = fma(c2, th.q[2][c], p0);
+        double p1 = c3 * th.q[3][c];
+        p1 = fma(c4, th.q[4][c], p1);
+        p1 = fma(c5, th.q[5][c], p1);
+        p1 = fma(c6, th.q[6][c], p1);
+        const double inner = fma(dth, p0 + p1, var2_state(th, VK_V0, c));
         th.xn[c] = fma(dth, inner, var2_state(th, VK_X0C, c));
     }
 }
 
-// partial predictor sum for substep m (1..7): everything but the term of g_{kl(m)}, whose PGX coefficient is zero
-template <int N, int P, int D>
-RV_D void var2_predictor_partial(Var2Thread<P, D>& th, int m, double (&pp)[P * D]) {
-    const double c0 = rvtabm::PGX[m][0], c1 = rvtabm::PGX[m][1], c2 = rvtabm::PGX[m][2], c3 = rvtabm::PGX[m][3],
-                 c4 = rvtabm::PGX[m][4], c5 = rvtabm::PGX[m][5], c6 = rvtabm::PGX[m][6];
-#pragma unroll
-    for (int c = 0; c < N; c++) {
-        double p0 = fma(c0, th.q[0][c], 0.5 * var2_state(th, VK_A0, c));
-        p0 = fma(c2, th.q[2][c], p0);
-        p0 = fma(c4, th.q[4][c], p0);
-        p0 = fma(c6, th.q[6][c], p0);
-        double p1 = c1 * th.q[1][c];
-        p1 = fma(c3, th.q[3][c], p1);
-        p1 = fma(c5, th.q[5][c], p1);
-        pp[c] = p0 + p1;
-    }
-}
-
-// corrector of substep n given the force an; also prepares the predictor of the next substep
-template <int N, int P, int D>
-RV_D void var2_corrector(Var2Thread<P, D>& th, int n, const double (&an)[P * D]) {
-    const double ga = rvtabm::GA[n];
-    const double b0 = rvtabm::GB[n][0], b1 = rvtabm::GB[n][1], b2 = rvtabm::GB[n][2], b3 = rvtabm::GB[n][3],
-                 b4 = rvtabm::GB[n][4], b5 = rvtabm::GB[n][5];
-    double ppn[P * D];
-    var2_predictor_partial<N>(th, n == 7 ? 1 : n + 1, ppn);
+template <int n, int N, int P, int D>
+RV_D void var2_corrector_n(Var2Thread<P, D>& th, const double (&an)[P * D]) {
     double mg = 0.0, ma = 0.0;
 #pragma unroll
     for (int c = 0; c < N; c++) {
-        double s0 = -var2_state(th, VK_A0, c) * ga;
-        s0 = fma(-th.q[0][c], b0, s0);
-        s0 = fma(-th.q[2][c], b2, s0);
-        s0 = fma(-th.q[4][c], b4, s0);
-        double s1 = -th.q[1][c] * b1;
-        s1 = fma(-th.q[3][c], b3, s1);
-        s1 = fma(-th.q[5][c], b5, s1);
-        const double gn = fma(an[c], ga, s0 + s1);
+        const double gk = an[c] - var2_state(th, VK_A0, c);
+        double gn;
+        if (n <= 2) {
+            gn = gk * rvtab::GA[n];
+            if (n == 2) gn = fma(-th.q[0][c], rvtab::GB[n][0], gn);
+        } else {
+            double s0 = gk * rvtab::GA[n], s1 = -th.q[1][c] * rvtab::GB[n][1];
+#pragma unroll
+            for (int i = 0; i < n - 1; i++) {
+                if (i == 1) continue;
+                if (i & 1) s1 = fma(-th.q[i][c], rvtab::GB[n][i], s1);
+                else s0 = fma(-th.q[i][c], rvtab::GB[n][i], s0);
+            }
+            gn = s0 + s1;
+        }
         if (n == 7) {
             const double ak = fabs(an[c]), dg = fabs(gn - th.q[6][c]);
             if (is_normal(ak) && ak > ma) ma = ak;
             if (is_normal(dg) && dg > mg) mg = dg;
         }
-        th.gnew[c] = gn;
-        th.pp[c] = ppn[c];
-    }
-    // g_{n-1} <- gn: the only place the substep index selects a register
-    switch (n) {
-#define RV_STORE_G(k) case k + 1: { _Pragma("unroll") for (int c = 0; c < N; c++) th.q[k][c] = th.gnew[c]; } break;
-        RV_STORE_G(0) RV_STORE_G(1) RV_STORE_G(2) RV_STORE_G(3) RV_STORE_G(4) RV_STORE_G(5)
-        default: { _Pragma("unroll") for (int c = 0; c < N; c++) th.q[6][c] = th.gnew[c]; } break;
-#undef RV_STORE_G
+        th.q[n - 1][c] = gn;
     }
     if (n == 7) { th.mon_g = mg; th.mon_a = ma; }
+}
+template <int N, int P, int D>
+RV_D void var2_corrector(Var2Thread<P, D>& th, int n, const double (&an)[P * D]) {
+    switch (n) {
+        case 1: var2_corrector_n<1, N>(th, an); break;
+        case 2: var2_corrector_n<2, N>(th, an); break;
+        case 3: var2_corrector_n<3, N>(th, an); break;
+        case 4: var2_corrector_n<4, N>(th, an); break;
+        case 5: var2_corrector_n<5, N>(th, an); break;
+        case 6: var2_corrector_n<6, N>(th, an); break;
+        default: var2_corrector_n<7, N>(th, an); break;
+    }
 }
 
 // Initial conditions of the lane's coordinates: the jet of the barycentric state with respect to the set's parameters
@@ -491,7 +479,7 @@ RV_D void var2_run_items(Exec& ex, const VarArgs& a, const Var2Layout& L, double
                 const int nc = NCOF(th);
 #pragma unroll
                 for (int c = 0; c < NC; c++) {
-                    th.xn[c] = x0[c]; th.pp[c] = 0.0; th.gnew[c] = 0.0;
+                    th.xn[c] = x0[c];
 #pragma unroll
                     for (int k = 0; k < 7; k++) th.q[k][c] = 0.0;
                     if (c < nc) {
@@ -533,11 +521,7 @@ RV_D void var2_run_items(Exec& ex, const VarArgs& a, const Var2Layout& L, double
                             for (int k = 6; k > j; k--) s = fma(th.q[k][cc], rvtab::DD[k][j], s);
                             th.q[j][cc] = s + th.q[j][cc];
                         }
-                        th.gnew[cc] = th.q[6][cc];
                     }
-                    // predictor partial sum of substep 1 (every term but g6's)
-                    if (th.role == 2) var2_predictor_partial<NC>(th, 1, th.pp);
-                    else var2_predictor_partial<D>(th, 1, th.pp);
                 });
                 Ratio pc_err{1e300, 1.0}, pc_last{2.0, 1.0};
                 int it = 0;

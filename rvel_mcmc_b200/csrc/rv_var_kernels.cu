@@ -239,7 +239,6 @@ cudaError_t launch_var(const VarArgs& a, int P, int D, int nv, int layout, int n
     if (layout != 1 && var2_supported(P, nv)) {
         const int nt = var2_min_threads(nv);
         if (P == 2 && D == 2 && nt <= 96) {                       // nv <= 10 (HD155358): 4 x 96 = 384 threads, 168 registers
-            if (layout == 2 && var2_groups(2, 2, nv, 96, 5) >= 5) return launch_var2_one<2, 2, 96, 5, 128>(a, nv, num_sms, stream);   // tuning
             if (var2_groups(2, 2, nv, 96, 4) >= 4) return launch_var2_one<2, 2, 96, 4, 168>(a, nv, num_sms, stream);
         }
         if (P == 2 && D == 2 && nt <= 160 && var2_groups(2, 2, nv, 160, 2) >= 2) return launch_var2_one<2, 2, 160, 2, 200>(a, nv, num_sms, stream);
