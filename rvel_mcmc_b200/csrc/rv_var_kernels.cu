@@ -241,7 +241,7 @@ cudaError_t launch_var(const VarArgs& a, int P, int D, int nv, int layout, int n
         if (P == 2 && D == 2 && nt <= 96) {                       // nv <= 10 (HD155358): 4 x 96 = 384 threads, 168 registers
             if (var2_groups(2, 2, nv, 96, 4) >= 4) return launch_var2_one<2, 2, 96, 4, 168>(a, nv, num_sms, stream);
         }
-        if (P == 2 && D == 2 && nt <= 160 && var2_groups(2, 2, nv, 160, 2) >= 2) return launch_var2_one<2, 2, 160, 2, 200>(a, nv, num_sms, stream);
+        // (a coplanar two-planet model has at most 10 free parameters, so 96 threads per group always suffice)
         if (P == 1 && D == 2 && nt <= 64) return launch_var2_one<1, 2, 64, 4, 128>(a, nv, num_sms, stream);
         if (P == 1 && D == 3 && nt <= 64) return launch_var2_one<1, 3, 64, 4, 168>(a, nv, num_sms, stream);
     }

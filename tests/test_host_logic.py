@@ -152,3 +152,18 @@ def test_ac_times_and_efficacy_definitions():
     t0 = datetime(2020, 1, 1)
     stamps = [t0, t0 + timedelta(seconds=3), t0 + timedelta(seconds=13)]
     assert abs(driver.efficacy(1000, [2.0, 5.0], stamps) - 1000 / (10.0 * 5.0)) < 1e-12      # from the SECOND stamp
+
+
+def test_fast_keyword_selects_dense_output_without_touching_the_callers_state():
+    """mcmc.Mh / Ensemble take fast=True (not in the reference): the sampler's own State copy evaluates the plain likelihood
+    with the dense-output option; the caller's State and the default behaviour are unchanged."""
+    from rvel_mcmc_b200 import mcmc, state
+    s = state.State([{"a": 0.2275, "h": 0., "k": 0., "m": 0.001965}], ignore_vars=["m"])
+    obs = object()
+    assert mcmc.Mh(s, obs).state.dense_output is False
+    mh = mcmc.Mh(s, obs, fast=True)
+    assert mh.state.dense_output is True and s.dense_output is False
+    assert mh.generate_proposal().dense_output is True           # proposals inherit it (State.deepcopy)
+    np.random.seed(1)
+    ens = mcmc.Ensemble(s, obs, {'a': 3e-4, 'h': 0.01, 'k': 0.01}, nwalkers=8, fast=True)
+    assert ens.state.dense_output is True and len(ens.states) == 8
