@@ -225,5 +225,12 @@ def test_device_group_single_process_multi_gpu():
         e1 = st._model(ctx).stretch_run(obs._handle(ctx), theta[:W], 5, seed=6, record_chain=False)
         assert np.array_equal(e["theta"], e1["theta"]) and np.array_equal(e["lnp"], e1["lnp"])
         assert np.array_equal(e["n_accept"], e1["n_accept"])
+        # with chain rows, thinning and a restart (first_step / lnp): same rows as the single-GPU call
+        ec = g.stretch_run(st, obs, theta[:W], 6, seed=6, thin=2, record_chain=True)
+        e1c = st._model(ctx).stretch_run(obs._handle(ctx), theta[:W], 6, seed=6, thin=2)
+        assert ec["chain"].shape == (3, W, 10) and np.array_equal(ec["chain"], e1c["chain"])
+        assert np.array_equal(ec["chain_lnp"], e1c["chain_lnp"]) and np.array_equal(ec["theta"], e1c["theta"])
+        er = g.stretch_run(st, obs, ec["chain"][0], 4, seed=6, first_step=2, lnp=ec["chain_lnp"][0])
+        assert np.array_equal(er["theta"], e1c["theta"]) and np.array_equal(er["lnp"], e1c["lnp"])
     finally:
         g.close()
