@@ -102,13 +102,15 @@ RV_HD double rinv3_scaled(double r2, double s) {
 }
 
 // u^(-1/7) for the IAS15 step-size controller (rebound: pow(epsilon/err, 1./7.)).  Device: single-precision seed and
-// three division-free Newton steps on y^-7 = u (y <- y (8 - u y^7)/7), ~25 FP64 instructions instead of pow()'s ~150.
+// two division-free Newton steps on y^-7 = u (y <- y (8 - u y^7)/7), ~15 FP64 instructions instead of pow()'s ~150.
 RV_HD double inv_root7(double u) {
 #if defined(__CUDA_ARCH__)
     if (!(u > 1e-30 && u < 1e30)) return pow(u, -1.0 / 7.0);
+    // seed: relative error <= ~6e-7 (float log2 of |log2 u| <= 100); Newton on y^-7 = u squares it with a factor 4:
+    // 1.4e-12 after one step, < 1e-23 after two
     double y = (double)exp2f(-log2f((float)u) * (1.0f / 7.0f));
 #pragma unroll
-    for (int k = 0; k < 3; k++) {
+    for (int k = 0; k < 2; k++) {
         const double y2 = y * y, y4 = y2 * y2;
         const double y7 = y4 * y2 * y;
         y = y * fma(-u, y7, 8.0) * (1.0 / 7.0);
@@ -312,7 +314,7 @@ struct Walker {
     double gmo[P > 1 ? P - 1 : 1], muo[P > 1 ? P - 1 : 1];
     double gm0;           // G*m_star
     double min2;          // exit_min_distance^2
-    double epsilon;
+    double inv_eps;       // 1 / epsilon (the step-size controller multiplies: one IEEE division less per attempt)
     bool star_in_norm;    // sum(mu) >= 1: the star can dominate the max-norms (never for planets)
     unsigned long long n_force, n_attempt;
 
@@ -498,7 +500,7 @@ struct Walker {
         gm0 = m0;
         const double emd = md->hill_factor * hill;
         min2 = emd * emd;
-        epsilon = md->epsilon;
+        inv_eps = 1.0 / md->epsilon;
         // move_to_com: the star sits at the origin before the shift
         double com_x[3], com_v[3];
 #pragma unroll

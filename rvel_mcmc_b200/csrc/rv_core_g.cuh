@@ -25,7 +25,7 @@ struct WalkerG : Walker<P, D, PL, VAR> {
     using B::mu;
     using B::x0; using B::v0; using B::a0; using B::ha0; using B::csx; using B::csv;
     using B::b;                       // holds b between attempts and g inside the predictor-corrector loop
-    using B::t; using B::dt; using B::dt_last_done; using B::grp; using B::hist; using B::epsilon;
+    using B::t; using B::dt; using B::dt_last_done; using B::grp; using B::hist; using B::inv_eps;
     using B::star_in_norm; using B::n_force; using B::n_attempt;
 
     // One Gauss-Radau substep, software-pipelined: the only predictor term on the dependency chain is the one of the g
@@ -101,24 +101,23 @@ struct WalkerG : Walker<P, D, PL, VAR> {
     }
 
     RV_D void predict_g(double q, const double (&_e)[7], const double (&_b)[7], int c) {
+        // rebound: ratio > 20 -> e = b = 0; written with selects (one straight-line block, no zero-fill branch)
+        const bool far = q > 20.0;
+        const double q1 = far ? 0.0 : q, q2 = q1 * q1, q3 = q1 * q2, q4 = q2 * q2, q5 = q2 * q3, q6 = q3 * q3, q7 = q3 * q4;
         double e[7];
-        if (q > 20.0) {
+        e[0] = q1 * (_b[6] * 7.0 + _b[5] * 6.0 + _b[4] * 5.0 + _b[3] * 4.0 + _b[2] * 3.0 + _b[1] * 2.0 + _b[0]);
+        e[1] = q2 * (_b[6] * 21.0 + _b[5] * 15.0 + _b[4] * 10.0 + _b[3] * 6.0 + _b[2] * 3.0 + _b[1]);
+        e[2] = q3 * (_b[6] * 35.0 + _b[5] * 20.0 + _b[4] * 10.0 + _b[3] * 4.0 + _b[2]);
+        e[3] = q4 * (_b[6] * 35.0 + _b[5] * 15.0 + _b[4] * 5.0 + _b[3]);
+        e[4] = q5 * (_b[6] * 21.0 + _b[5] * 6.0 + _b[4]);
+        e[5] = q6 * (_b[6] * 7.0 + _b[5]);
+        e[6] = q7 * _b[6];
 #pragma unroll
-            for (int k = 0; k < 7; k++) { e[k] = 0.0; b[k][c] = 0.0; }
-        } else {
-            const double q1 = q, q2 = q1 * q1, q3 = q1 * q2, q4 = q2 * q2, q5 = q2 * q3, q6 = q3 * q3, q7 = q3 * q4;
-            e[0] = q1 * (_b[6] * 7.0 + _b[5] * 6.0 + _b[4] * 5.0 + _b[3] * 4.0 + _b[2] * 3.0 + _b[1] * 2.0 + _b[0]);
-            e[1] = q2 * (_b[6] * 21.0 + _b[5] * 15.0 + _b[4] * 10.0 + _b[3] * 6.0 + _b[2] * 3.0 + _b[1]);
-            e[2] = q3 * (_b[6] * 35.0 + _b[5] * 20.0 + _b[4] * 10.0 + _b[3] * 4.0 + _b[2]);
-            e[3] = q4 * (_b[6] * 35.0 + _b[5] * 15.0 + _b[4] * 5.0 + _b[3]);
-            e[4] = q5 * (_b[6] * 21.0 + _b[5] * 6.0 + _b[4]);
-            e[5] = q6 * (_b[6] * 7.0 + _b[5]);
-            e[6] = q7 * _b[6];
-#pragma unroll
-            for (int k = 0; k < 7; k++) b[k][c] = e[k] + (_b[k] - _e[k]);
+        for (int k = 0; k < 7; k++) {
+            e[k] = far ? 0.0 : e[k];                    // (0 * b is not 0 for a non-finite b)
+            b[k][c] = e[k] + (far ? 0.0 : (_b[k] - _e[k]));
+            hist.at((14 + k) * NC + c) = e[k];
         }
-#pragma unroll
-        for (int k = 0; k < 7; k++) hist.at((14 + k) * NC + c) = e[k];
     }
 
     // One IAS15 step attempt; same contract as Walker::attempt.
@@ -157,7 +156,9 @@ struct WalkerG : Walker<P, D, PL, VAR> {
         int it = 0;
         bool iterating = active;
         while (true) {
-            if (iterating && (ratio_lt(pc_err, 1e-16) || (it > 2 && ratio_le(pc_last, pc_err)) || it >= 12)) iterating = false;
+            // rebound's stopping rule, evaluated without short-circuit branches (three predicates, one vote)
+            const bool stop = ratio_lt(pc_err, 1e-16) | ((it > 2) & ratio_le(pc_last, pc_err)) | (it >= 12);
+            iterating = iterating & !stop;
             if (!warp_any(iterating)) break;
             if (iterating) { pc_last = pc_err; it++; }
             substep_g<1>(iterating, x0c, xp, at, dg6, pp);
@@ -235,7 +236,7 @@ struct WalkerG : Walker<P, D, PL, VAR> {
             const double err = maxb6 / maxak;
             const double dt_done = dt;
             double dt_new;
-            if (is_normal(err)) dt_new = inv_root7(err / epsilon) * dt_done;
+            if (is_normal(err)) dt_new = inv_root7(err * inv_eps) * dt_done;
             else dt_new = dt_done * 4.0;
             if (fabs(dt_new) < 0.25 * fabs(dt_done)) {
                 dt = dt_new;
