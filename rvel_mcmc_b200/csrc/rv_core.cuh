@@ -66,6 +66,18 @@ RV_HD bool is_normal(double x) {
     return a >= DBL_MIN && a <= DBL_MAX;
 }
 
+// m = max(m, a) over the NORMAL values only (rebound's isnormal() guards in the IAS15 norms); a = |x| (or NaN), m >= 0.
+// Device: exponent-field test and ordering on the integer pipe (for non-negative doubles the IEEE order is the integer order)
+// -- the FP64 pipe, which bounds the kernels, is spared three DSETP per value.
+RV_HD void norm_max(double a, double& m) {
+#if defined(__CUDA_ARCH__)
+    const unsigned e = ((unsigned)__double2hiint(a) & 0x7ff00000u) - 0x00100000u;   // exponent field 1..0x7fe <=> e < 0x7fe00000
+    if (e < 0x7fe00000u && __double_as_longlong(a) > __double_as_longlong(m)) m = a;
+#else
+    if (is_normal(a) && a > m) m = a;
+#endif
+}
+
 // 1/r^3 from r^2.
 RV_HD double rinv3(double r2) {
 #if defined(__CUDA_ARCH__)

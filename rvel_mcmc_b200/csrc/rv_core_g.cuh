@@ -21,6 +21,9 @@ struct WalkerG : Walker<P, D, PL, VAR> {
     static constexpr int HIST = 21;   // doubles of shared-memory history per coordinate: er[7], br[7], e[7]
     static constexpr int DENSE0 = HIST * NC;               // then 9 per own planet: v0x, a0x, b0x..b6x of the last step
     static constexpr bool kDense = (VAR & 4) != 0;         // dense-output instantiation (model option dense_output)
+    // off-chain sums of a substep: one accumulator (fewest FP64 instructions: +1 % in the default mode, which is bound by
+    // FP64-pipe throughput) or two (shorter chains: +4 % in the dense-output mode); measured, profiles/r02p_loglik_variants.txt
+    static constexpr bool kSplitAcc = kDense;
     static constexpr int LANE_DOUBLES = HIST * NC + (kDense ? 9 * PL : 0);   // shared-memory doubles per lane
     using B::mu;
     using B::x0; using B::v0; using B::a0; using B::ha0; using B::csx; using B::csv;
@@ -50,6 +53,19 @@ struct WalkerG : Walker<P, D, PL, VAR> {
         // off the dependency chain of the force evaluation below
 #pragma unroll
         for (int c = 0; c < NC; c++) {
+          if constexpr (!kSplitAcc) {
+            double s0 = -a0[c] * tGA<VAR>(n);
+#pragma unroll
+            for (int i = 0; i < n - 1; i++) s0 = fma(-b[i][c], tGB<VAR>(n, i), s0);
+            sc[c] = s0;
+            double q0 = ha0[c];
+#pragma unroll
+            for (int k = 0; k < 7; k++) {
+                if (k == n - 1) continue;
+                q0 = fma(tPG<VAR>(m, k), b[k][c], q0);
+            }
+            ppn[c] = q0;
+          } else {
             double s0 = -a0[c] * tGA<VAR>(n), s1 = 0.0;
 #pragma unroll
             for (int i = 0; i < n - 1; i++) {
@@ -65,6 +81,7 @@ struct WalkerG : Walker<P, D, PL, VAR> {
                 else q0 = fma(tPG<VAR>(m, k), b[k][c], q0);
             }
             ppn[c] = q0 + q1;
+          }
         }
         this->accel(xn, an);
 #pragma unroll
@@ -143,14 +160,12 @@ struct WalkerG : Walker<P, D, PL, VAR> {
 #pragma unroll
         for (int c = 0; c < NC; c++) {
             xp[c] = x0[c]; at[c] = a0[c]; dg6[c] = 0.0;
-            // predictor partial sum of substep 1: every term but g6's (see substep_g)
-            double q0 = ha0[c], q1 = 0.0;
+            // predictor partial sum of substep 1: every term but g6's (see substep_g); a0/2 joins last, so that the sums
+            // over g run while the force evaluation above is still in flight
+            double q0 = tPG<VAR>(1, 0) * b[0][c];
 #pragma unroll
-            for (int k = 0; k < 6; k++) {
-                if (k & 1) q1 = fma(tPG<VAR>(1, k), b[k][c], q1);
-                else q0 = fma(tPG<VAR>(1, k), b[k][c], q0);
-            }
-            pp[c] = q0 + q1;
+            for (int k = 1; k < 6; k++) q0 = fma(tPG<VAR>(1, k), b[k][c], q0);
+            pp[c] = q0 + ha0[c];
         }
         Ratio pc_err{1e300, 1.0}, pc_last{2.0, 1.0};
         int it = 0;
@@ -172,15 +187,14 @@ struct WalkerG : Walker<P, D, PL, VAR> {
 #pragma unroll
             for (int c = 0; c < NC; c++) {
                 const double ak = fabs(at[c]), dg = fabs(dg6[c]);
-                if (is_normal(ak) && ak > maxat) maxat = ak;
-                if (is_normal(dg) && dg > maxdg) maxdg = dg;
+                norm_max(ak, maxat);
+                norm_max(dg, maxdg);
             }
             if (warp_any(star_in_norm)) {
 #pragma unroll
                 for (int d = 0; d < D; d++) {
                     const double sa = fabs(this->template star_of<true>(at, d)), sg = fabs(this->template star_of<true>(dg6, d));
-                    if (star_in_norm && is_normal(sa) && sa > maxat) maxat = sa;
-                    if (star_in_norm && is_normal(sg) && sg > maxdg) maxdg = sg;
+                    if (star_in_norm) { norm_max(sa, maxat); norm_max(sg, maxdg); }
                 }
             }
             maxdg = grp.template gmax<true>(maxdg);
@@ -210,8 +224,7 @@ struct WalkerG : Walker<P, D, PL, VAR> {
 #pragma unroll
             for (int d = 0; d < D; d++) {
                 const double ak = fabs(at[pl * D + d]), b6 = fabs(b[6][pl * D + d]);
-                if (keep && is_normal(ak) && ak > maxak) maxak = ak;
-                if (keep && is_normal(b6) && b6 > maxb6) maxb6 = b6;
+                if (keep) { norm_max(ak, maxak); norm_max(b6, maxb6); }
             }
         }
         if (warp_any(star_in_norm)) {
@@ -225,19 +238,33 @@ struct WalkerG : Walker<P, D, PL, VAR> {
             const bool keep = star_in_norm && !(fabs(v2 * dt * dt) < 1e-16 * x2);
 #pragma unroll
             for (int d = 0; d < D; d++) {
-                if (keep && is_normal(sa[d]) && sa[d] > maxak) maxak = sa[d];
-                if (keep && is_normal(sb[d]) && sb[d] > maxb6) maxb6 = sb[d];
+                if (keep) { norm_max(sa[d], maxak); norm_max(sb[d], maxb6); }
             }
         }
         maxak = grp.template gmax<true>(maxak);
         maxb6 = grp.template gmax<true>(maxb6);
+        // the position / velocity increments of this step (used if it is accepted): they depend on b only, so they are
+        // formed here, beside the latency chain of the step-size controller (shuffles, division, seventh root)
+        double sx[NC], sv[NC];
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+            double s = b[6][c] * (1. / 72.);
+            s = fma(b[5][c], 1. / 56., s); s = fma(b[4][c], 1. / 42., s); s = fma(b[3][c], 1. / 30., s);
+            s = fma(b[2][c], 1. / 20., s); s = fma(b[1][c], 1. / 12., s); s = fma(b[0][c], 1. / 6., s);
+            sx[c] = fma(a0[c], 0.5, s);
+            double u = b[6][c] * (1. / 8.);
+            u = fma(b[5][c], 1. / 7., u); u = fma(b[4][c], 1. / 6., u); u = fma(b[3][c], 1. / 5., u);
+            u = fma(b[2][c], 1. / 4., u); u = fma(b[1][c], 1. / 3., u); u = fma(b[0][c], 1. / 2., u);
+            sv[c] = u + a0[c];
+        }
         int result = 0;
         if (active) {
             const double err = maxb6 / maxak;
             const double dt_done = dt;
-            double dt_new;
-            if (is_normal(err)) dt_new = inv_root7(err * inv_eps) * dt_done;
-            else dt_new = dt_done * 4.0;
+            // ratio = dt_new / dt_done as the controller produces it (rebound divides the product again; same to 1 ulp)
+            double ratio = 4.0;
+            if (is_normal(err)) ratio = inv_root7(err * inv_eps);
+            double dt_new = ratio * dt_done;
             if (fabs(dt_new) < 0.25 * fabs(dt_done)) {
                 dt = dt_new;
                 if (dt_last_done != 0.0) {
@@ -253,7 +280,7 @@ struct WalkerG : Walker<P, D, PL, VAR> {
                     // no history yet: rebound retries with the b it holds (the corrected ones)
                 }
             } else {
-                if (fabs(dt_new) > 4.0 * fabs(dt_done)) dt_new = dt_done * 4.0;      // same sign: dt_new/dt_done > 1/safety
+                if (fabs(dt_new) > 4.0 * fabs(dt_done)) { dt_new = dt_done * 4.0; ratio = 4.0; }   // same sign: dt_new/dt_done > 1/safety
                 dt = dt_new;
                 const double dt2 = dt_done * dt_done;
                 if constexpr (kDense) {
@@ -269,28 +296,20 @@ struct WalkerG : Walker<P, D, PL, VAR> {
                 for (int c = 0; c < NC; c++) {
                     {
                         const double a = x0[c];
-                        double s = b[6][c] * (1. / 72.);
-                        s = fma(b[5][c], 1. / 56., s); s = fma(b[4][c], 1. / 42., s); s = fma(b[3][c], 1. / 30., s);
-                        s = fma(b[2][c], 1. / 20., s); s = fma(b[1][c], 1. / 12., s); s = fma(b[0][c], 1. / 6., s);
-                        s = fma(a0[c], 0.5, s);
-                        csx[c] += fma(s, dt2, v0[c] * dt_done);
+                        csx[c] += fma(sx[c], dt2, v0[c] * dt_done);
                         x0[c] = a + csx[c];
                         csx[c] += a - x0[c];
                     }
                     {
                         const double a = v0[c];
-                        double s = b[6][c] * (1. / 8.);
-                        s = fma(b[5][c], 1. / 7., s); s = fma(b[4][c], 1. / 6., s); s = fma(b[3][c], 1. / 5., s);
-                        s = fma(b[2][c], 1. / 4., s); s = fma(b[1][c], 1. / 3., s); s = fma(b[0][c], 1. / 2., s);
-                        s += a0[c];
-                        csv[c] = fma(s, dt_done, csv[c]);
+                        csv[c] = fma(sv[c], dt_done, csv[c]);
                         v0[c] = a + csv[c];
                         csv[c] += a - v0[c];
                     }
                 }
                 t += dt_done;
                 dt_last_done = dt_done;
-                const double q = dt / dt_done;
+                const double q = ratio;
 #pragma unroll
                 for (int c = 0; c < NC; c++) {
                     double _e[7], _b[7];

@@ -572,8 +572,8 @@ RV_D void var_run_items(Exec& ex, const VarArgs& a, const VarLayout& L, double* 
 #pragma unroll
                             for (int cc = 0; cc < D; cc++) {
                                 const double ak = fabs(th.at[cc]), dg = fabs(th.dg6[cc]);
-                                if (is_normal(ak) && ak > ma) ma = ak;
-                                if (is_normal(dg) && dg > mg) mg = dg;
+                                norm_max(ak, ma);
+                                norm_max(dg, mg);
                             }
                         }
                         ex.stage_max(th, mg, ma);
@@ -608,8 +608,8 @@ RV_D void var_run_items(Exec& ex, const VarArgs& a, const VarLayout& L, double* 
 #pragma unroll
                         for (int cc = 0; cc < D; cc++) {
                             const double ak = fabs(th.at[cc]), b6 = fabs(th.q[6][cc]);
-                            if (keep && is_normal(ak) && ak > ma) ma = ak;
-                            if (keep && is_normal(b6) && b6 > mb) mb = b6;
+                            if (keep) norm_max(ak, ma);
+                            if (keep) norm_max(b6, mb);
                         }
                     }
                     ex.stage_max(th, mb, ma);

@@ -286,8 +286,8 @@ RV_D void var2_corrector_n(Var2Thread<P, D>& th, const double (&an)[P * D]) {
         }
         if (n == 7) {
             const double ak = fabs(an[c]), dg = fabs(gn - th.q[6][c]);
-            if (is_normal(ak) && ak > ma) ma = ak;
-            if (is_normal(dg) && dg > mg) mg = dg;
+            norm_max(ak, ma);
+            norm_max(dg, mg);
         }
         th.q[n - 1][c] = gn;
     }
@@ -592,8 +592,8 @@ RV_D void var2_run_items(Exec& ex, const VarArgs& a, const Var2Layout& L, double
 #pragma unroll
                         for (int d = 0; d < D; d++) {
                             const double ak = fabs(realv[th.planet * D + d]), b6 = fabs(th.q[6][d]);
-                            if (keep && is_normal(ak) && ak > ma) ma = ak;
-                            if (keep && is_normal(b6) && b6 > mb) mb = b6;
+                            if (keep) norm_max(ak, ma);
+                            if (keep) norm_max(b6, mb);
                         }
                     }
                     ex.stage_max(th, mb, ma);
