@@ -324,6 +324,7 @@ struct Walker {
     double gm[PL];        // G*m of own planets
     double mu[PL];        // m/m_star of own planets
     double gmo[P > 1 ? P - 1 : 1], muo[P > 1 ? P - 1 : 1];
+    double mu1;           // PL == 1: 1 + mu of the own planet
     double gm0;           // G*m_star
     double min2;          // exit_min_distance^2
     double inv_eps;       // 1 / epsilon (the step-size controller multiplies: one IEEE division less per attempt)
@@ -334,21 +335,21 @@ struct Walker {
     // Runs only inside the warp-uniform attempt body (full-mask shuffles).
     RV_D void accel(const double (&x)[NC], double (&a)[NC]) {
         if constexpr (PL == 1) {
+            // planet - star separation ds = x + sum_j mu_j x_j = (1 + mu_own) x + sum_others mu_o x_o  (mu1 = 1 + mu_own)
             double xo[P > 1 ? P - 1 : 1][D];
-            double S[D];
+            double ds[D], r2 = 0.0;
 #pragma unroll
-            for (int d = 0; d < D; d++) S[d] = mu[0] * x[d];
+            for (int d = 0; d < D; d++) ds[d] = mu1 * x[d];
 #pragma unroll
             for (int o = 0; o < P - 1; o++) {
 #pragma unroll
                 for (int d = 0; d < D; d++) {
                     xo[o][d] = grp.template ahead<true>(x[d], o + 1);
-                    S[d] = fma(muo[o], xo[o][d], S[d]);
+                    ds[d] = fma(muo[o], xo[o][d], ds[d]);
                 }
             }
-            double ds[D], r2 = 0.0;
 #pragma unroll
-            for (int d = 0; d < D; d++) { ds[d] = x[d] + S[d]; r2 = fma(ds[d], ds[d], r2); }
+            for (int d = 0; d < D; d++) r2 = fma(ds[d], ds[d], r2);
             const double ks = rinv3_scaled(r2, -gm0);
 #pragma unroll
             for (int d = 0; d < D; d++) a[d] = ks * ds[d];
@@ -492,6 +493,7 @@ struct Walker {
             pal_to_cart(el[pl], m0, xr[pl], vr[pl]);
             gm[pl] = el[pl][EL_M];
             mu[pl] = el[pl][EL_M] / m0;
+            if (PL == 1) mu1 = 1.0 + mu[pl];
             msum += el[pl][EL_M];
             const double rh = el[pl][EL_A] * pow(el[pl][EL_M] / (3.0 * m0), 1.0 / 3.0);
             if (rh > hill) hill = rh;
