@@ -150,10 +150,10 @@ struct WalkerG : Walker<P, D, PL, VAR> {
             // g from b, in place (g_j needs b_k for k > j only)
 #pragma unroll
             for (int j = 0; j < 7; j++) {
-                double s = 0.0;
+                double s = b[j][c];
 #pragma unroll
                 for (int k = 6; k > j; k--) s = fma(b[k][c], tDD<VAR>(k, j), s);
-                b[j][c] = s + b[j][c];
+                b[j][c] = s;
             }
         }
         double xp[NC], at[NC], dg6[NC], pp[NC];
@@ -207,10 +207,10 @@ struct WalkerG : Walker<P, D, PL, VAR> {
         for (int c = 0; c < NC; c++) {
 #pragma unroll
             for (int k = 0; k < 7; k++) {
-                double s = 0.0;
+                double s = b[k][c];
 #pragma unroll
                 for (int j = 6; j > k; j--) s = fma(b[j][c], tCC<VAR>(j, k), s);
-                b[k][c] = s + b[k][c];
+                b[k][c] = s;
             }
         }
         // step-size control

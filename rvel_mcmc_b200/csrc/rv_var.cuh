@@ -542,10 +542,10 @@ RV_D void var_run_items(Exec& ex, const VarArgs& a, const VarLayout& L, double* 
                         // g from b, in place (g_j needs b_k for k > j only)
 #pragma unroll
                         for (int j = 0; j < 7; j++) {
-                            double s = 0.0;
+                            double s = th.q[j][cc];
 #pragma unroll
                             for (int k = 6; k > j; k--) s = fma(th.q[k][cc], rvtab::DD[k][j], s);
-                            th.q[j][cc] = s + th.q[j][cc];
+                            th.q[j][cc] = s;
                         }
                     }
                 });
@@ -593,10 +593,10 @@ RV_D void var_run_items(Exec& ex, const VarArgs& a, const VarLayout& L, double* 
                         for (int cc = 0; cc < D; cc++) {
 #pragma unroll
                             for (int k = 0; k < 7; k++) {
-                                double s = 0.0;
+                                double s = th.q[k][cc];
 #pragma unroll
                                 for (int j = 6; j > k; j--) s = fma(th.q[j][cc], rvtab::CC[j][k], s);
-                                th.q[k][cc] = s + th.q[k][cc];
+                                th.q[k][cc] = s;
                             }
                         }
                     }

@@ -516,10 +516,10 @@ RV_D void var2_run_items(Exec& ex, const VarArgs& a, const Var2Layout& L, double
                         ST(th, K_X0C, cc) = x0[cc] - ST(th, K_CSX, cc);
 #pragma unroll
                         for (int j = 0; j < 7; j++) {      // g from b, in place
-                            double s = 0.0;
+                            double s = th.q[j][cc];
 #pragma unroll
                             for (int k = 6; k > j; k--) s = fma(th.q[k][cc], rvtab::DD[k][j], s);
-                            th.q[j][cc] = s + th.q[j][cc];
+                            th.q[j][cc] = s;
                         }
                     }
                 });
@@ -577,10 +577,10 @@ RV_D void var2_run_items(Exec& ex, const VarArgs& a, const Var2Layout& L, double
                             if (cc >= nc) break;
 #pragma unroll
                             for (int k = 0; k < 7; k++) {
-                                double s = 0.0;
+                                double s = th.q[k][cc];
 #pragma unroll
                                 for (int j = 6; j > k; j--) s = fma(th.q[j][cc], rvtab::CC[j][k], s);
-                                th.q[k][cc] = s + th.q[k][cc];
+                                th.q[k][cc] = s;
                             }
                         }
                     }
