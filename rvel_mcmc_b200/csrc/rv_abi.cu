@@ -396,6 +396,9 @@ static int var_dev_impl(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, c
     const int nv = model->h.nvars;
     if (model->h.integrator != 0)
         return fail(ctx, -31, "the variational (gradient + Hessian) path integrates with IAS15 only; set integrator = 0");
+    if (model->h.P > rv::MAXP_VAR)
+        return fail(ctx, -30, "variational kernel: built for up to %d planets (this model has %d); the plain likelihood, MH and the stretch move take up to %d",
+                    rv::MAXP_VAR, model->h.P, rv::MAXP);
     const bool set_per_lane = model->var_layout == 0 && model->h.P <= 2 && model->h.D == 2 && nv + 1 <= 32;
     if (!set_per_lane && rv::var_threads_needed(model->h.P, nv) > 448)
         return fail(ctx, -30, "variational kernel: %d planets x %d free parameters need %d (set, planet) threads; the limit is 448",

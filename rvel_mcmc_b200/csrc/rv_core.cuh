@@ -29,7 +29,8 @@
 
 namespace rv {
 
-constexpr int MAXP = 3;            // planets per system supported by the compiled kernels
+constexpr int MAXP = 5;            // planets per system supported by the compiled plain-likelihood kernels
+constexpr int MAXP_VAR = 3;        // ... by the variational (gradient + Hessian) kernels
 constexpr int NELEM = 7;           // m, a, h, k, l, ix, iy
 constexpr int MAXV = MAXP * NELEM; // free parameters
 

@@ -115,6 +115,11 @@ static cudaError_t launch_loglik_var(const LoglikArgs& a, int P, int D, int mapp
         case 231: return launch_one<2, 3, 1, 128, 2, VAR>(a, num_sms, stream);
         case 320: case 321: return launch_one<3, 2, 1, 128, 3, VAR>(a, num_sms, stream);
         case 330: case 331: return launch_one<3, 3, 1, 128, 2, VAR>(a, num_sms, stream);
+        // four and five planets: lane per planet only (8 / 6 walkers per warp)
+        case 420: case 421: return launch_one<4, 2, 1, 128, 2, VAR>(a, num_sms, stream);
+        case 430: case 431: return launch_one<4, 3, 1, 128, 2, VAR>(a, num_sms, stream);
+        case 520: case 521: return launch_one<5, 2, 1, 128, 2, VAR>(a, num_sms, stream);
+        case 530: case 531: return launch_one<5, 3, 1, 128, 2, VAR>(a, num_sms, stream);
         default: return cudaErrorInvalidValue;
     }
 }

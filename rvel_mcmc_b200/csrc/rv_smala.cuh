@@ -10,7 +10,7 @@
 
 namespace rv {
 
-constexpr int SMAX = MAXV;   // 21
+constexpr int SMAX = MAXP_VAR * NELEM;   // 21: SMALA needs the variational kernels
 
 // Cyclic Jacobi eigen-decomposition of the symmetric n x n matrix A (row-major, destroyed): A -> diag(lam), Q columns.
 RV_HD bool jacobi_eig(int n, double* A, double* Q, double* lam) {

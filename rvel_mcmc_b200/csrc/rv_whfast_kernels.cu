@@ -33,6 +33,10 @@ cudaError_t launch_whfast(const WhArgs& a, int P, int D, int num_sms, cudaStream
         case 23: return launch_wh_one<2, 3>(a, num_sms, stream);
         case 32: return launch_wh_one<3, 2>(a, num_sms, stream);
         case 33: return launch_wh_one<3, 3>(a, num_sms, stream);
+        case 42: return launch_wh_one<4, 2>(a, num_sms, stream);
+        case 43: return launch_wh_one<4, 3>(a, num_sms, stream);
+        case 52: return launch_wh_one<5, 2>(a, num_sms, stream);
+        case 53: return launch_wh_one<5, 3>(a, num_sms, stream);
         default: return cudaErrorInvalidValue;
     }
 }

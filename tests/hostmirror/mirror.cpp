@@ -69,6 +69,10 @@ extern "C" int mirror_loglik(int P, const double* fixed, int nvars, const int* f
         case 23: run<2, 3>(a); break;
         case 32: run<3, 2>(a); break;
         case 33: run<3, 3>(a); break;
+        case 42: run<4, 2>(a); break;
+        case 43: run<4, 3>(a); break;
+        case 52: run<5, 2>(a); break;
+        case 53: run<5, 3>(a); break;
         default: return -9;
     }
     if (times) {

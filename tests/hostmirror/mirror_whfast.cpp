@@ -35,6 +35,10 @@ extern "C" int mirror_whfast(int P, const double* fixed, int nvars, const int* f
             case 23: rv::whfast_item<2, 3>(a, it); break;
             case 32: rv::whfast_item<3, 2>(a, it); break;
             case 33: rv::whfast_item<3, 3>(a, it); break;
+            case 42: rv::whfast_item<4, 2>(a, it); break;
+            case 43: rv::whfast_item<4, 3>(a, it); break;
+            case 52: rv::whfast_item<5, 2>(a, it); break;
+            case 53: rv::whfast_item<5, 3>(a, it); break;
             default: return -9;
         }
     }

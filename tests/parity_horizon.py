@@ -51,6 +51,10 @@ def problem(name):
     if name == "c4":             # configs[3] shape: three planets, 15 free parameters
         obs, fixed, center, sc = T.c4_problem()
         return obs, fixed, T.FP15, T.FE15, 2.0, center, sc
+    if name in ("four", "five"):  # beyond the BASELINE configs: four / five planets, 20 / 25 free parameters
+        obs, fixed, fp, fe, center, sc = T.many_planet_problem(4 if name == "four" else 5)
+        # (hill factor 1 for five planets: twice the outermost planet's Hill radius exceeds the spacing of the inner pair)
+        return obs, fixed, fp, fe, (2.0 if name == "four" else 1.0), center, sc
     raise KeyError(name)
 
 

@@ -310,3 +310,32 @@ def c4_problem(nper=40, tmax=30.0, seed=17, err=1.5e-4):
     center = np.array([[p[k] for k in ("a", "h", "k", "m", "l")] for p in C4_PLANETS]).reshape(-1)
     scale_vec = np.array([C4_SCALES[k] for k in ("a", "h", "k", "m", "l")] * 3)
     return obs, np.zeros((3, 7)), center, scale_vec
+
+
+# ---- beyond the BASELINE configs: the reference's schema is open in the number of planets (state.py:8-31) ----------------
+FIVE_PLANETS = [{"m": 0.92e-3, "a": 0.2275, "h": -0.06, "k": 0.015, "l": -1.0},
+                {"m": 1.95e-3, "a": 0.3665, "h": 0.02, "k": 0.0, "l": 2.1},
+                {"m": 1.1e-3, "a": 0.59, "h": 0.01, "k": 0.03, "l": 0.4},
+                {"m": 0.6e-3, "a": 0.95, "h": -0.02, "k": 0.01, "l": 2.9},
+                {"m": 0.3e-3, "a": 1.55, "h": 0.03, "k": -0.02, "l": -2.2}]
+
+
+def many_planet_problem(npl, nper=30, tmax=24.0, seed=23, err=1.5e-4):
+    """(obs, fixed[npl][7], fp, fe, center[5 npl], scale_vec[5 npl]) for the first npl of FIVE_PLANETS, all (a, h, k, m, l) free."""
+    rng = np.random.RandomState(seed)
+    planets = FIVE_PLANETS[:npl]
+    obs = Obs()
+    obs.tf = np.append([0.0], np.sort(rng.uniform(0, tmax / 2, nper)))
+    obs.tb = np.sort(rng.uniform(-tmax / 2, 0, nper))
+    E = elems_from_planets(planets)
+    st, rvf = orc_rv(E, 0.0, obs.tf)
+    st2, rvb = orc_rv(E, 0.0, obs.tb)
+    assert st == 0 and st2 == 0
+    obs.errorf = np.full(nper + 1, err); obs.errorb = np.full(nper, err)
+    obs.rvf = rvf + err * rng.normal(size=nper + 1); obs.rvb = rvb + err * rng.normal(size=nper)
+    obs.Npoints = 2 * nper
+    fp = [p for p in range(npl) for _ in range(5)]
+    fe = [1, 2, 3, 0, 4] * npl
+    center = np.array([[p[k] for k in ("a", "h", "k", "m", "l")] for p in planets]).reshape(-1)
+    scale_vec = np.array([C4_SCALES[k] for k in ("a", "h", "k", "m", "l")] * npl)
+    return obs, np.zeros((npl, 7)), fp, fe, center, scale_vec

@@ -137,3 +137,34 @@ def test_mirror_dense_output_option():
     assert c1[1] < 0.7 * c0[1]
     assert (s2 == 0).all() and np.abs(l2 - lo2).max() < 1e-9 * np.abs(lo2).max() and c2[1] < 0.6 * co2[1]
     assert list(s3) == [3, 3, 3]
+
+
+FIVE_PLANETS = [{"m": 0.92e-3, "a": 0.2275, "h": -0.06, "k": 0.015, "l": -1.0},
+                {"m": 1.95e-3, "a": 0.3665, "h": 0.02, "k": 0.0, "l": 2.1},
+                {"m": 1.1e-3, "a": 0.59, "h": 0.01, "k": 0.03, "l": 0.4},
+                {"m": 0.6e-3, "a": 0.95, "h": -0.02, "k": 0.01, "l": 2.9},
+                {"m": 0.3e-3, "a": 1.55, "h": 0.03, "k": -0.02, "l": -2.2}]
+
+
+def test_mirror_four_and_five_planets():
+    # the reference's schema is open in the number of planets (state.py:8-31); the plain engine is built for up to five
+    rng = np.random.RandomState(5)
+    obs = T.Obs()
+    obs.tf = np.append([0], np.sort(rng.uniform(0, 5.0, 12))); obs.tb = np.sort(rng.uniform(0, -5.0, 12))
+    obs.rvf = 1e-4 * rng.normal(size=13); obs.rvb = 1e-4 * rng.normal(size=12)
+    obs.errorf = np.full(13, 3e-4); obs.errorb = np.full(12, 3e-4); obs.Npoints = 24
+    for npl, incl in ((4, False), (5, False), (4, True), (5, True)):
+        planets = [dict(p) for p in FIVE_PLANETS[:npl]]
+        if incl:
+            for i, p in enumerate(planets):
+                p["ix"] = 0.02 * (i + 1); p["iy"] = -0.015 * (i - 1)
+        E = T.elems_from_planets(planets)
+        # free parameters: a, m of every planet, drawn in a small ball
+        fp = [i for i in range(npl) for _ in range(2)]; fe = [1, 0] * npl
+        center = np.array([[p["a"], p["m"]] for p in planets]).reshape(-1)
+        theta = center[None, :] * (1.0 + 1e-3 * rng.normal(size=(3, 2 * npl)))
+        lo, so, co = T.orc_logp_batch(E, fp, fe, 1.0, obs, theta)
+        lm, sm, cm = T.mirror_loglik(E, fp, fe, 1.0, obs, theta)
+        assert np.array_equal(so, sm) and (so == 0).all()
+        assert np.abs(lm - lo).max() < 1e-9 * np.abs(lo).max()
+        assert abs(co[1] - cm[1]) <= 3

@@ -75,3 +75,16 @@ def test_device_engine_statuses_and_other_shapes():
     rv_m, sm, _ = T.mirror_whfast(E, [], [], 1.0, 0.01, None, np.zeros((1, 0)), times=times)
     assert st == 0 and sm[0] == 0
     assert np.abs(rv_m[0] - rv_o).max() < 1e-12
+
+
+def test_device_engine_four_and_five_planets():
+    # the WHFast engine instantiated for four / five planets (Jacobi chain of any length) against its oracle
+    for npl in (4, 5):
+        obs, fixed, fp, fe, center, sc = T.many_planet_problem(npl, nper=10, tmax=8.0)
+        theta = T.gaussian_ball(center, sc, 3, 9, width=1e-3)
+        dt = 2 * np.pi * 0.2275 ** 1.5 / 20
+        lo, so, co = T.orc_whfast_logp_batch(fixed, fp, fe, 1.0, dt, obs, theta)
+        lm, sm, cm = T.mirror_whfast(fixed, fp, fe, 1.0, dt, obs, theta)
+        assert np.array_equal(so, sm) and (so == 0).all()
+        assert co[1] == cm[1]
+        assert np.abs(lm - lo).max() < 1e-9 * max(1.0, np.abs(lo).max())
