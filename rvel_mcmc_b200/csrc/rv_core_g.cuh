@@ -118,8 +118,10 @@ struct WalkerG : Walker<P, D, PL, VAR> {
     }
 
     RV_D void predict_g(double q, const double (&_e)[7], const double (&_b)[7], int c) {
-        // rebound: ratio > 20 -> e = b = 0; written with selects (one straight-line block, no zero-fill branch)
+        // rebound: ratio > 20 -> e = b = 0.  Branch-free and select-free: q -> 0 zeroes every e, keep = 0 drops (b - e_old)
+        // (for finite coefficients; a walker with non-finite coefficients is already on its way to ST_NONFINITE)
         const bool far = q > 20.0;
+        const double keep = far ? 0.0 : 1.0;
         const double q1 = far ? 0.0 : q, q2 = q1 * q1, q3 = q1 * q2, q4 = q2 * q2, q5 = q2 * q3, q6 = q3 * q3, q7 = q3 * q4;
         double e[7];
         e[0] = q1 * (_b[6] * 7.0 + _b[5] * 6.0 + _b[4] * 5.0 + _b[3] * 4.0 + _b[2] * 3.0 + _b[1] * 2.0 + _b[0]);
@@ -131,8 +133,7 @@ struct WalkerG : Walker<P, D, PL, VAR> {
         e[6] = q7 * _b[6];
 #pragma unroll
         for (int k = 0; k < 7; k++) {
-            e[k] = far ? 0.0 : e[k];                    // (0 * b is not 0 for a non-finite b)
-            b[k][c] = e[k] + (far ? 0.0 : (_b[k] - _e[k]));
+            b[k][c] = fma(keep, _b[k] - _e[k], e[k]);
             hist.at((14 + k) * NC + c) = e[k];
         }
     }

@@ -39,6 +39,7 @@ def main():
     ap.add_argument("--out", default="")
     ap.add_argument("--update", default="")
     ap.add_argument("--note", default="")
+    ap.add_argument("--walkers", type=int, default=0, help="walkers of the profiled launch (stored with --update)")
     a = ap.parse_args()
     raw = subprocess.run(["ncu", "-i", a.report, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
@@ -78,6 +79,8 @@ def main():
                         "issue_active_pct": float(last["smsp__issue_active.avg.pct_of_peak_sustained_active"][0]),
                         "registers_per_thread": int(float(last["launch__registers_per_thread"][0])),
                         "gpu_time_ms": t_ms, "source": a.out or a.report, "note": a.note}
+        if a.walkers:
+            ri[a.update]["walkers_per_launch"] = a.walkers
         with open(path, "w") as f:
             json.dump(ri, f, indent=2)
             f.write("\n")
