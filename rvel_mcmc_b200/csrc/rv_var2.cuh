@@ -28,7 +28,7 @@ struct Var2Layout {
     int nps;           // planet slots: nsets * P (so lane t, planet p -> p * n2 + t; producer lane (s, p) -> n2 * P + s * P + p)
     int CB;            // doubles per producer-set block in a buffer: P*D positions + D star sum
     int cstride;       // doubles per buffer: (nv + 1) * CB, rounded up to even
-    int o_cbuf, o_dm, o_red, o_real, o_mbar, o_uni, o_state, total;   // offsets in doubles (per group)
+    int o_cbuf, o_dm, o_dg, o_red, o_real, o_mbar, o_uni, o_state, total;   // offsets in doubles (per group)
 };
 constexpr int VAR2_STATE_PER_COORD = 13;   // shared memory, per coordinate: x0, csx, csv, x0c, v0, a0, e[7]
 // Each planet slot owns one contiguous block [entry k][axis d] of an ODD number of doubles: a lane reaches every entry from
@@ -52,6 +52,7 @@ RV_HD Var2Layout var2_layout(int P, int D, int nv, int NT = 0) {
     int o = 0;
     L.o_cbuf = o; o += 8 * L.cstride;      // buffer 0: positions at x0; 1..7: predicted at substep n (1.. reused for the epoch exchange)
     L.o_dm = o; o += (nv > 0 ? nv : 1) * P; if (o & 1) o++;
+    L.o_dg = o; o += (nv > 0 ? nv : 1) * P; if (o & 1) o++;   // d(G m_j) / d(parameter): 1 where the parameter is that mass
     L.o_red = o; o += 2 * 2 * 8 + 2;        // ping-pong group maxima (up to 8 warps) + the item broadcast slot
     L.o_real = o; o += P * D; if (o & 1) o++;      // the real lanes' last force (step-size control)
     L.o_mbar = o; o += 8;                   // seven substep mbarriers (8 bytes each)
@@ -178,6 +179,7 @@ RV_D void var2_fence() {
 template <int P, int D>
 RV_D void var2_force_second(const double (&xu)[P * D], const double* __restrict__ X0, const double* __restrict__ XA,
                             const double* __restrict__ XB, const double* __restrict__ dma, const double* __restrict__ dmb,
+                            const double* __restrict__ dga, const double* __restrict__ dgb,
                             const VarUniform<P>& u, double (&an)[P * D]) {
     double SU[D];
 #pragma unroll
@@ -199,11 +201,13 @@ RV_D void var2_force_second(const double (&xu)[P * D], const double* __restrict_
             r2 = fma(dd[d], dd[d], r2); da = fma(dd[d], A[d], da); db = fma(dd[d], B[d], db);
             ab = fma(A[d], B[d], ab); du = fma(dd[d], U[d], du);
         }
-        const double y = rinv1(r2), y2 = y * y, r3i = y * y2, r5i = r3i * y2, r7i = r5i * y2;
-        const double c5 = -3.0 * r5i;
-        const double m = u.gm0;
-        const double kU = m * r3i, kA = m * c5 * db, kB = m * c5 * da;
-        const double kd = m * fma(c5, du + ab, 15.0 * r7i * (da * db));
+        // m / r^3, -3 m / r^5 and 15 m / r^7 = (-3 m / r^5)(-5 / r^2): the mass rides on the first power (12 scalar
+        // operations instead of 15)
+        const double y = rinv1(r2), y2 = y * y;
+        const double kU = (y * u.gm0) * y2;
+        const double c5m = kU * (-3.0 * y2);
+        const double kA = c5m * db, kB = c5m * da;
+        const double kd = c5m * fma(-5.0 * y2, da * db, du + ab);
 #pragma unroll
         for (int d = 0; d < D; d++) an[i * D + d] = -fma(kU, U[d], fma(kA, A[d], fma(kB, B[d], kd * dd[d])));
         var2_fence();
@@ -221,11 +225,12 @@ RV_D void var2_force_second(const double (&xu)[P * D], const double* __restrict_
                 r2 = fma(dd[d], dd[d], r2); da = fma(dd[d], A[d], da); db = fma(dd[d], B[d], db);
                 ab = fma(A[d], B[d], ab); du = fma(dd[d], U[d], du);
             }
-            const double y = rinv1(r2), y2 = y * y, r3i = y * y2, r5i = r3i * y2, r7i = r5i * y2;
-            const double c5 = -3.0 * r5i;
-            const double g0 = fma(c5, du + ab, 15.0 * r7i * (da * db));   // coefficient of m d
+            const double y = rinv1(r2), y2 = y * y, r3i = y * y2;
+            const double c5 = r3i * (-3.0 * y2);
+            const double g0 = c5 * fma(-5.0 * y2, da * db, du + ab);      // coefficient of m d
             const double c5db = c5 * db, c5da = c5 * da;
-            const double dgaj = dma[j] * u.gm0, dgbj = dmb[j] * u.gm0, dgai = dma[i] * u.gm0, dgbi = dmb[i] * u.gm0;
+            // dga / dgb: derivative of G m_j with respect to the parents' parameters (1 where the parameter is that mass)
+            const double dgaj = dga[j], dgbj = dgb[j], dgai = dga[i], dgbi = dgb[i];
             {   // side i: masses of j
                 const double m = u.gm[j];
                 const double kU = m * r3i, kA = fma(m, c5db, dgbj * r3i), kB = fma(m, c5da, dgaj * r3i);
@@ -366,6 +371,7 @@ RV_D void var2_run_items(Exec& ex, const VarArgs& a, const Var2Layout& L, double
     double* const cbuf = sm + L.o_cbuf;
     double* const vxs = cbuf + L.cstride;          // the epoch exchange reuses the substep buffers (dead between steps)
     double* const dm = sm + L.o_dm;
+    double* const dg = sm + L.o_dg;
     double* const realv = sm + L.o_real;
     double* const state = sm + L.o_state;
     const double m0 = md->m_star;
@@ -391,6 +397,7 @@ RV_D void var2_run_items(Exec& ex, const VarArgs& a, const Var2Layout& L, double
         if (th.tid < nv * P) {
             const int q = th.tid / P, j = th.tid - q * P;
             dm[th.tid] = (md->free_planet[q] == j && md->free_elem[q] == EL_M) ? 1.0 / m0 : 0.0;
+            dg[th.tid] = (md->free_planet[q] == j && md->free_elem[q] == EL_M) ? 1.0 : 0.0;
         }
     });
 
@@ -462,7 +469,7 @@ RV_D void var2_run_items(Exec& ex, const VarArgs& a, const Var2Layout& L, double
             auto force = [&](const Var2Thread<P, D>& th, int b, const double (&x)[NC], double (&an)[NC]) {
                 const double* Xr = cbuf + b * L.cstride;
                 if (th.role == 2) {
-                    var2_force_second<P, D>(x, Xr, Xr + th.oa, Xr + th.ob, dm + th.pa * P, dm + th.pb * P, u, an);
+                    var2_force_second<P, D>(x, Xr, Xr + th.oa, Xr + th.ob, dm + th.pa * P, dm + th.pb * P, dg + th.pa * P, dg + th.pb * P, u, an);
                 } else {
                     double S[D], SU[D];
 #pragma unroll
