@@ -77,7 +77,7 @@ def test_model_validation(ctx):
         with pytest.raises(_abi.RvGpuError):
             _abi.ModelHandle(ctx, Z2, bad["fp"], bad["fe"], 1.0)
     with pytest.raises(_abi.RvGpuError):
-        _abi.ModelHandle(ctx, np.zeros((4, 7)), [], [], 1.0)       # more than 3 planets
+        _abi.ModelHandle(ctx, np.zeros((_abi.MAX_PLANETS + 1, 7)), [], [], 1.0)       # more than RV_MAX_PLANETS planets
     m = _m(ctx, Z2, T.FP10, T.FE10, 2.0)
     with pytest.raises(_abi.RvGpuError):
         m.set_option("no_such_option", 1)
