@@ -73,6 +73,28 @@ def var_flops_per_eval(S, T, nv=10, N=3):
     return S * (3 * (30 + nv * 45 + n2 * 140) + coords * 36) + T * coords * 150
 
 
+_STDOUT_FD = None
+
+
+def quiet_stdout():
+    """stdout carries exactly ONE JSON line (the driver parses it): from here on everything any library writes to file
+    descriptor 1 (the NCCL version banner, NCCL_DEBUG output, warnings printed from native code) goes to stderr instead."""
+    global _STDOUT_FD
+    if _STDOUT_FD is None:
+        sys.stdout.flush()
+        _STDOUT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_line(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _STDOUT_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_STDOUT_FD, data)
+
+
 def roofline_inputs():
     """Figures that only a profiler can give (DRAM traffic per launch, FP64-pipe utilisation): read from ONE committed
     file that names the ncu summary each comes from -- never typed into this script."""
@@ -306,7 +328,7 @@ def run_stretch_sharded(ctx, model, oh, rank, world, dist, dev, torch, nsteps):
              "allgather_ms_per_half_step": gath, "host_and_idle_ms_per_half_step": max(0.0, per_half - kern - gath),
              "allgather_bytes_per_half_step": h * 10 * 8,
              "items_per_gpu_per_half_step": 2 * n_loc, "resident_item_slots_per_gpu": slots}
-        d["limiter"] = ("kernel: one half-step cannot be shorter than the serial IAS15 integration of its longest leg (~8-9 ms for "
+        d["limiter"] = ("kernel: one half-step cannot be shorter than the serial IAS15 integration of its longest leg (~5 ms for "
                         "HD155358's 1244-step backward leg); %d items for %d resident slots per GPU"
                         % (2 * n_loc, slots)) if kern > 4 * gath else "exchange"
         out[label] = d
@@ -356,7 +378,7 @@ def run_reference(args):
                              "sample": "%d walkers x %d steps, oracle/rv_oracle.c (gcc -O3 -march=native, OpenMP, %d threads)" % (sample, args.steps, cores)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit_line(line)
 
 
 def main():
@@ -379,6 +401,7 @@ def main():
     ap.add_argument("--sharded-steps", type=int, default=6)
     ap.add_argument("--quick", action="store_true", help="smoke-sized side blocks (200 ESS rows, no CPU baseline)")
     args = ap.parse_args()
+    quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
         return
@@ -396,7 +419,6 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG", "WARN")        # keep stdout to the one JSON line
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -585,7 +607,7 @@ def main():
         line["var"] = var_block
     if sharded is not None:
         line["stretch_sharded"] = sharded
-    print(json.dumps(line))
+    emit_line(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
