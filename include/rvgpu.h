@@ -90,7 +90,9 @@ int rv_model_destroy(rv_model* model);
  *   most negative epoch, the order state.py:273 uses: about half the backward steps, logp equal to ~1e-11),
  * "dense_output" (0 = every hop ends exactly on its epoch, rebound's exact_finish_time = 1; 1 = rv_loglik integrates each
  *   leg once with natural IAS15 steps and reads the RV at every epoch from the step's acceleration polynomial: the
- *   number of steps no longer grows with the number of epochs; implies monotone_backward; logp equal to ~1e-10)      */
+ *   number of steps no longer grows with the number of epochs; implies monotone_backward; logp equal to ~1e-10),
+ * "cost_order" (1 = batches of >= 4096 walkers are integrated most-expensive-first, walkers of similar cost side by side
+ *   (key: max over planets of the pericentre distance^-3/2); scheduling only -- results are bit-identical to 0)      */
 int rv_model_set_option(rv_model* model, const char* key, double value);
 
 /* ---- State.get_logp (state.py:103-110) for W parameter vectors; HOST buffers -------------------- */

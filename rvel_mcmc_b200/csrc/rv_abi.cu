@@ -25,6 +25,8 @@ struct rv_ctx {
     double* d_logp; size_t cap_logp;
     int* d_status; size_t cap_status;
     double* d_part; size_t cap_part;
+    int* d_order; size_t cap_order;       // cost-ordered scheduling: order[W], then bin[W]
+    int* d_costhist;                      // [2 * RV_COST_BINS]: histogram (kept zero between calls), cursors
     int* d_pstat; size_t cap_pstat;
     double* d_times; size_t cap_times;
     double* d_rv; size_t cap_rv;
@@ -61,6 +63,7 @@ struct rv_model {
     rv::Model* d;
     int mapping;
     int var_layout;    // 0 automatic, 1 thread per (set, planet) -- see launch_var
+    int cost_order;    // 1 (default): the likelihood kernel takes its items most expensive first (launch_cost_order)
 };
 
 static char g_err[512] = "";
@@ -160,7 +163,7 @@ int rv_ctx_destroy(rv_ctx* c) {
     cudaStreamSynchronize(c->stream);
     cudaFree(c->d_item_counter); cudaFree(c->d_work);
     cudaFree(c->d_theta); cudaFree(c->d_logp); cudaFree(c->d_status); cudaFree(c->d_part);
-    cudaFree(c->d_pstat); cudaFree(c->d_times); cudaFree(c->d_rv);
+    cudaFree(c->d_pstat); cudaFree(c->d_times); cudaFree(c->d_rv); cudaFree(c->d_order); cudaFree(c->d_costhist);
     cudaFree(c->d_prop); cudaFree(c->d_plogp); cudaFree(c->d_pstatus); cudaFree(c->d_zz); cudaFree(c->d_scales);
     cudaFree(c->d_chain); cudaFree(c->d_chainlp); cudaFree(c->d_nacc); cudaFree(c->d_acc);
     cudaFree(c->d_vpart); cudaFree(c->d_grad); cudaFree(c->d_hess);
@@ -217,7 +220,7 @@ int rv_model_create(rv_ctx* ctx, int n_planets, const double* fixed, int nvars, 
     if (!ctx || !out || !fixed) return fail(ctx, -1, "rv_model_create: NULL argument");
     rv_model* m = new (std::nothrow) rv_model();
     if (!m) return fail(ctx, -12, "out of host memory");
-    m->ctx = ctx; m->mapping = 0; m->var_layout = 0; m->d = nullptr;
+    m->ctx = ctx; m->mapping = 0; m->var_layout = 0; m->cost_order = 1; m->d = nullptr;
     const int rc = rv::build_model(&m->h, n_planets, fixed, nvars, free_planet, free_elem, hill_factor, dims);
     if (rc) {
         delete m;
@@ -248,6 +251,7 @@ int rv_model_set_option(rv_model* m, const char* key, double value) {
     else if (!strcmp(key, "hill_factor")) m->h.hill_factor = value;
     else if (!strcmp(key, "mapping")) m->mapping = (int)value;
     else if (!strcmp(key, "var_layout")) m->var_layout = (int)value;
+    else if (!strcmp(key, "cost_order")) m->cost_order = value != 0.0;
     else if (!strcmp(key, "check_prior")) m->h.check_prior = value != 0.0;
     else if (!strcmp(key, "monotone_backward")) m->h.monotone_backward = value != 0.0;
     else if (!strcmp(key, "dense_output")) m->h.dense_output = value != 0.0;
@@ -285,6 +289,17 @@ static int loglik_dev_impl(rv_ctx* ctx, const rv_model* model, const rv_obs* obs
     a.part_chi2 = ctx->d_part; a.part_status = ctx->d_pstat;
     a.item_counter = ctx->d_item_counter;
     a.work_counters = ctx->count_work ? ctx->d_work : nullptr;
+    // batches of more than one wave of items: most expensive walkers first, similar walkers adjacent
+    if (model->cost_order && W >= 4096 && W < (int64_t)1 << 31) {
+        if (int rc = ensure(ctx, &ctx->d_order, &ctx->cap_order, (size_t)(2 * W))) return rc;
+        if (!ctx->d_costhist) {
+            CU(ctx, cudaMalloc((void**)&ctx->d_costhist, 2 * rv::RV_COST_BINS * sizeof(int)));
+            CU(ctx, cudaMemsetAsync(ctx->d_costhist, 0, 2 * rv::RV_COST_BINS * sizeof(int), s));
+        }
+        CU(ctx, rv::launch_cost_order(model->d, d_theta, W, ctx->d_order + W, ctx->d_costhist, ctx->d_costhist + rv::RV_COST_BINS,
+                                      ctx->d_order, s));
+        a.order = ctx->d_order;
+    }
     CU(ctx, rv::launch_loglik(a, model->h.P, model->h.D, model->mapping, model->h.dense_output, ctx->num_sms, s));
     CU(ctx, rv::launch_finalize(ctx->d_part, ctx->d_pstat, W, obs->npoints, d_logp, d_status, ctx->d_item_counter, s));
     return 0;

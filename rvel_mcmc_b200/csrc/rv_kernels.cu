@@ -152,6 +152,89 @@ cudaError_t launch_curve_finalize(unsigned long long* item_counter, cudaStream_t
     return cudaGetLastError();
 }
 
+// ---- cost-ordered scheduling ---------------------------------------------------------------------------------------
+// The number of IAS15 steps of a walker is set by its fastest pericentre passage: max_p a_p^-3/2 (1 - e_p)^-3/2 tracks the
+// measured step count of posterior walkers with rank correlation 0.95 (HD155358 ensemble).  Walkers are binned by that key
+// (1/32 octave), most expensive first, and the likelihood kernel takes its items in that order: the lane groups of a warp
+// then integrate walkers of similar cost and stay in step (a warp runs every predictor-corrector loop for the slowest of its
+// groups: lane efficiency 0.77 -> 0.88 on the equilibrated ensemble), and the launch ends on its cheapest items.  A counting
+// sort in three small kernels; the order inside a bin is whatever the atomics give -- it affects scheduling only, results are
+// stored by walker.
+constexpr int COST_BINS = RV_COST_BINS;
+
+__global__ void cost_bin_kernel(const Model* __restrict__ md, const double* __restrict__ theta, long long W,
+                                int* __restrict__ bin, int* __restrict__ hist) {
+    const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= W) return;
+    const int P = md->P, nv = md->nvars;
+    float key = 0.0f;
+    bool bad = false;
+    for (int i = 0; i < P; i++) {
+        float el[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const int e = EL_A + k;                        // a, h, k
+            const int sidx = md->src[i * NELEM + e];
+            el[k] = (float)((sidx >= 0) ? theta[w * nv + sidx] : md->fixed[i * NELEM + e]);
+        }
+        const float e2 = el[1] * el[1] + el[2] * el[2];
+        if (!(el[0] > 0.02f) || !(e2 < 1.0f)) bad = true;  // hard prior: the item returns at once
+        const float q = el[0] * (1.0f - sqrtf(fminf(e2, 0.9801f)));          // pericentre distance
+        const float c = rsqrtf(q) / q;                     // q^-3/2
+        key = fmaxf(key, c);
+    }
+    int b = COST_BINS - 1;                                 // cheapest bin: prior violations, non-finite keys
+    if (!bad && key > 0.0f && key < 3.0e38f) {
+        const float l = (log2f(key) + 12.0f) * 32.0f;      // 2^-12 .. 2^20 in 1/32 octaves
+        const int i = l < 0.0f ? 0 : (l > (float)(COST_BINS - 2) ? COST_BINS - 2 : (int)l);
+        b = COST_BINS - 2 - i;                             // most expensive first
+    }
+    bin[w] = b;
+    // one atomic per distinct bin of the warp (a start ball puts every walker into the same two or three bins)
+    const unsigned peers = __match_any_sync(__activemask(), b);
+    if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[b], __popc(peers));
+}
+
+// exclusive prefix sum of the histogram -> per-bin cursors; clears the histogram for the next call
+__global__ void __launch_bounds__(COST_BINS) cost_scan_kernel(int* __restrict__ hist, int* __restrict__ cursor) {
+    __shared__ int sh[COST_BINS];
+    const int t = threadIdx.x;
+    const int v = hist[t];
+    sh[t] = v;
+    __syncthreads();
+    for (int o = 1; o < COST_BINS; o <<= 1) {
+        const int x = t >= o ? sh[t - o] : 0;
+        __syncthreads();
+        sh[t] += x;
+        __syncthreads();
+    }
+    cursor[t] = sh[t] - v;
+    hist[t] = 0;
+}
+
+__global__ void cost_scatter_kernel(const int* __restrict__ bin, long long W, int* __restrict__ cursor, int* __restrict__ order) {
+    const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= W) return;
+    const int b = bin[w];
+    const unsigned peers = __match_any_sync(__activemask(), b);
+    const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(&cursor[b], __popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    order[base + __popc(peers & ((1u << lane) - 1u))] = (int)w;
+}
+
+// order[W] from theta; bin[W], hist[COST_BINS] (zero on entry, zero on exit), cursor[COST_BINS]: scratch
+cudaError_t launch_cost_order(const Model* md, const double* theta, long long W, int* bin, int* hist, int* cursor, int* order,
+                              cudaStream_t stream) {
+    const int nt = 256;
+    const unsigned nb = (unsigned)((W + nt - 1) / nt);
+    cost_bin_kernel<<<nb, nt, 0, stream>>>(md, theta, W, bin, hist);
+    cost_scan_kernel<<<1, COST_BINS, 0, stream>>>(hist, cursor);
+    cost_scatter_kernel<<<nb, nt, 0, stream>>>(bin, W, cursor, order);
+    return cudaGetLastError();
+}
+
 // ---- State.setup_sim (state.py:36-47) made visible: barycentric particles [W][P+1][7] = m, x, y, z, vx, vy, vz ----
 // One thread per walker; the same Pal -> cartesian and move_to_com arithmetic the integrating kernels start from.
 __global__ void initial_conditions_kernel(const Model* __restrict__ md, const double* __restrict__ theta, long long W,

@@ -11,6 +11,9 @@ struct Model;
 cudaError_t launch_initial_conditions(const Model* md, const double* theta, long long W, double* out, int* status,
                                       cudaStream_t stream);
 cudaError_t launch_fp64_peak(double* d_out, int blocks, int iters, cudaStream_t stream);
+constexpr int RV_COST_BINS = 1024;
+cudaError_t launch_cost_order(const Model* md, const double* theta, long long W, int* bin, int* hist, int* cursor, int* order,
+                              cudaStream_t stream);
 // variational path (rv_var_kernels.cu)
 struct VarArgs;
 int var_threads_needed(int P, int nv);

@@ -14,6 +14,10 @@ struct LoglikArgs {
     const Model* model;
     const double* theta;      // [W][nvars] row-major
     long long W;
+    // optional scheduling order: the i-th item of a leg is walker order[i] (most expensive first, walkers of similar cost
+    // adjacent: the lane groups of a warp then stay in step, see cost_order in rv_kernels.cu); null = identity.  Results are
+    // stored by walker, so the order never shows in the output.
+    const int* order;
     // observation epochs: forward leg [0,nf), backward leg [nf,nf+nb) (order of obs.tf / obs.tb)
     const double* ot;
     const double* orv;
@@ -47,15 +51,15 @@ RV_D void run_items(WK& w, const LoglikArgs& a, const double* st, const double* 
     double sgn = 1.0;       // dense output: direction of the leg's single integration
     bool rev = false;       // this item visits its epochs in reversed storage order
     int phase = lane_active ? PH_NEED_ITEM : PH_DONE;
-    long long item = -1, wi = 0;
+    long long item = -1, wi = 0, slot = 0;   // slot: where this item's partial results go (leg * W + walker)
     const double *lt = nullptr, *lrv = nullptr, *lerr = nullptr;
     LegCursor c;
     c.status = RUN; c.ie = 0; c.n = 0; c.attempts = 0; c.tmax = 0.0; c.last_full_dt = 0.0; c.chi2 = 0.0;
 
     auto finish = [&](int status) {
         if (leader) {
-            a.part_status[item] = status;
-            if (!curve) a.part_chi2[item] = c.chi2;
+            a.part_status[slot] = status;
+            if (!curve) a.part_chi2[slot] = c.chi2;
 #if defined(__CUDA_ARCH__)
             if (a.work_counters) {
                 atomicAdd(&a.work_counters[0], w.n_force);
@@ -74,11 +78,13 @@ RV_D void run_items(WK& w, const LoglikArgs& a, const double* st, const double* 
                 item = fetch(w.grp);
                 if (item >= n_items) { phase = PH_DONE; break; }
                 if (curve) {
-                    wi = item; lt = a.times; lrv = nullptr; lerr = nullptr; c.n = a.nt; rev = false;
+                    wi = item; slot = item; lt = a.times; lrv = nullptr; lerr = nullptr; c.n = a.nt; rev = false;
                 } else if (item < a.W) {       // backward legs first: they are the longer ones
-                    wi = item; lt = st + a.nf; lrv = srv + a.nf; lerr = serr + a.nf; c.n = a.nb; rev = mono;
+                    wi = a.order ? (long long)a.order[item] : item; slot = wi;
+                    lt = st + a.nf; lrv = srv + a.nf; lerr = serr + a.nf; c.n = a.nb; rev = mono;
                 } else {
-                    wi = item - a.W; lt = st; lrv = srv; lerr = serr; c.n = a.nf; rev = false;
+                    wi = a.order ? (long long)a.order[item - a.W] : item - a.W; slot = a.W + wi;
+                    lt = st; lrv = srv; lerr = serr; c.n = a.nf; rev = false;
                 }
                 w.n_force = 0; w.n_attempt = 0;
                 c.ie = 0; c.chi2 = 0.0; c.attempts = 0;

@@ -275,3 +275,36 @@ def test_dense_output_option_matches_default(ctx):
         m2.set_option("dense_output", 1)
         l2, s2 = m2.loglik(oh, theta[:256])
         assert np.array_equal(s2, s1[:256]) and np.abs(l2[ok[:256]] - l1[:256][ok[:256]]).max() < 1e-8
+
+
+def test_cost_ordered_schedule_changes_nothing_but_the_order(ctx):
+    # batches of >= 4096 walkers are scheduled most-expensive-first (model option cost_order, default on): the order in which
+    # the kernel takes its items must never show in the results -- wide ball with prior violations and Encounters, the
+    # equilibrated posterior ensemble, three planets, and the samplers built on the same launch
+    import os
+    obs = T.load_vels("HD155358.vels")
+    oh = _obs_handle(ctx, obs)
+    m = _model(ctx, np.zeros((2, 7)), T.FP10, T.FE10, 2.0)
+    ens = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hd155358_equilibrated_ensemble.npy"))
+    theta = np.vstack([T.gaussian_ball(T.HD_SOL, T.HD_SCALE_VEC, 6000, 31, width=12.0), ens[:6000]])
+    theta[17, 3] = 1e-6; theta[18, 0] = 0.01; theta[19, 1] = np.nan
+    m.set_option("cost_order", 0)
+    l0, s0 = m.loglik(oh, theta)
+    m.set_option("cost_order", 1)
+    l1, s1 = m.loglik(oh, theta)
+    assert np.array_equal(s0, s1) and np.array_equal(l0, l1)
+    assert (s0 == 3).sum() > 0 and (s0 == 1).sum() > 0 and (s0 == 0).sum() > 6000
+    # the same walkers in a small batch (below the ordering threshold) and against the oracle
+    l2, s2 = m.loglik(oh, theta[6000:6256])
+    assert np.array_equal(l2, l1[6000:6256]) and np.array_equal(s2, s1[6000:6256])
+    lo, so, _ = T.orc_logp_batch(np.zeros((2, 7)), T.FP10, T.FE10, 2.0, obs, theta[5990:6010])
+    assert np.array_equal(so, s1[5990:6010])
+    ok = so == 0
+    assert np.abs(lo[ok] - l1[5990:6010][ok]).max() < 1e-6
+    # MH chains: 4096 chains in one call (ordered) == the same chains in two shards of 2048 (not ordered)
+    sc = np.array(T.HD_SCALE_VEC)
+    r = m.mh_run(oh, ens[:4096], sc, 0.02, 3, seed=9, record_chain=False, record_accepts=True)
+    ra = m.mh_run(oh, ens[:2048], sc, 0.02, 3, seed=9, record_chain=False, record_accepts=True)
+    rb = m.mh_run(oh, ens[2048:4096], sc, 0.02, 3, seed=9, first_chain_id=2048, record_chain=False, record_accepts=True)
+    assert np.array_equal(r["theta"], np.vstack([ra["theta"], rb["theta"]]))
+    assert np.array_equal(r["accepted"], np.hstack([ra["accepted"], rb["accepted"]]))

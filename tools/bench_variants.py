@@ -18,6 +18,7 @@ W = int(os.environ.get("WALKERS", "65536"))
 theta = torch.from_numpy(T.gaussian_ball(T.HD_SOL, T.HD_SCALE_VEC, W, 1001)).cuda()
 logp = torch.empty(W, dtype=torch.float64, device="cuda"); st = torch.empty(W, dtype=torch.int32, device="cuda")
 s = torch.cuda.current_stream().cuda_stream
+m.set_option("cost_order", int(os.environ.get("COST_ORDER", "1")))     # cost-ordered item schedule (default on)
 ref = None
 for mp in [int(x) for x in sys.argv[1:]] or [0]:
     m.set_option("mapping", mp)
