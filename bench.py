@@ -597,7 +597,8 @@ def main():
                        "walkers_per_gpu": W, "epochs": 122, "nvars": 10, "integrator": "ias15", "l2": "flushed between steps",
                        "mapping": "lane-per-planet" if args.mapping == 0 else "thread-per-walker", "ok_fraction": ok_frac},
             "e2e": {"value": n_total / e2e_s, "unit": UNIT, "h2d_bytes_per_step": W * 10 * 8, "d2h_bytes_per_step": W * 12},
-            "gpu_launches": 2 * args.steps, "clocks": sampler.summary(), "roofline": roofline}
+            # per step: cost_bin / cost_scan / cost_scatter (item order, W >= 4096), loglik_kernel, finalize_kernel
+            "gpu_launches": (5 if W >= 4096 else 2) * args.steps, "clocks": sampler.summary(), "roofline": roofline}
     line["non_default_options"] = options
     if cpu_baseline:
         line["cpu_baseline"] = cpu_baseline
