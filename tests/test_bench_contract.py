@@ -43,7 +43,7 @@ def test_gpu_arm_line():
                    "--ess-budget", "4,3,4"], 900)
     assert COMMON <= set(d) and "impl" not in d
     assert d["n_gpus"] == 1 and d["steps"] == 3 and d["warmup"] == 3 and d["scaling"] == "weak" and d["dtype"] == "f64"
-    assert d["gpu_launches"] == 6 and d["value"] > 1e5
+    assert d["gpu_launches"] == 15 and d["value"] > 1e5          # 3 steps x (3 item-order kernels + likelihood + finalize)
     assert d["e2e"]["h2d_bytes_per_step"] == 8192 * 80 and d["e2e"]["d2h_bytes_per_step"] == 8192 * 12 and d["e2e"]["value"] > 1e5
     rf = d["roofline"]
     assert rf["bound"] == "fp64_fma_pipe" and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-12 and rf["unit"] == "TFLOP/s"
