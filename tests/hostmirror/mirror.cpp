@@ -34,7 +34,8 @@ void run(const rv::LoglikArgs& a) {
 }
 }  // namespace
 
-static int g_monotone = 0, g_dense = 0;
+static int g_monotone = 0, g_dense = 0, g_reverse = 0;
+extern "C" void mirror_set_reverse_order(int v) { g_reverse = v; }   // items taken in reversed walker order (LoglikArgs::order)
 extern "C" void mirror_set_monotone(int v) { g_monotone = v; }
 extern "C" void mirror_set_dense(int v) { g_dense = v; }
 
@@ -61,6 +62,9 @@ extern "C" int mirror_loglik(int P, const double* fixed, int nvars, const int* f
     a.times = times; a.nt = nt; a.rv_out = rv_out;
     a.part_chi2 = part.data(); a.part_status = pst.data();
     a.item_counter = &ctr; a.work_counters = work;
+    std::vector<int> order((size_t)W);
+    for (long long w = 0; w < W; w++) order[(size_t)w] = (int)(W - 1 - w);
+    if (g_reverse && !times) a.order = order.data();
     const int key = P * 10 + m.D;
     switch (key) {
         case 12: run<1, 2>(a); break;

@@ -168,3 +168,20 @@ def test_mirror_four_and_five_planets():
         assert np.array_equal(so, sm) and (so == 0).all()
         assert np.abs(lm - lo).max() < 1e-9 * np.abs(lo).max()
         assert abs(co[1] - cm[1]) <= 3
+
+
+def test_mirror_item_order_does_not_show_in_the_results():
+    # LoglikArgs::order (the cost-ordered schedule of the device launch): items are taken in another order, results are stored
+    # by walker -- identical output, prior violations and Encounters included
+    obs, theta = _hd(5, 13)
+    theta = np.vstack([theta, np.array([k[0] for k in T.KAT5])])
+    theta[1, 3] = 1e-6
+    E = np.zeros((2, 7))
+    l0, s0, c0 = T.mirror_loglik(E, T.FP10, T.FE10, 2.0, obs, theta)
+    T.mirror().mirror_set_reverse_order(1)
+    try:
+        l1, s1, c1 = T.mirror_loglik(E, T.FP10, T.FE10, 2.0, obs, theta)
+    finally:
+        T.mirror().mirror_set_reverse_order(0)
+    assert np.array_equal(s0, s1) and np.array_equal(l0, l1) and list(c0) == list(c1)
+    assert list(s0[[1, 5, 6, 7]]) == [1, 3, 3, 3]
