@@ -395,7 +395,8 @@ def main():
     ap.add_argument("--ess", action="store_true", help="(default on; kept for compatibility)")
     ap.add_argument("--ess-rows", type=int, default=2000, help="recorded rows (= sampler steps) per ESS run (fewer if the "
                                                                "per-sampler time budget says so; the line reports it)")
-    ap.add_argument("--ess-budget", default="150,80,130", help="seconds for the stretch, MH and SMALA ESS runs")
+    ap.add_argument("--ess-budget", default=None, help="seconds for the stretch, MH and SMALA ESS runs (default 150,80,130 on "
+                                                       "one GPU; 90,50,80 at N > 1, where the driver's per-N limit is tighter)")
     ap.add_argument("--no-var", action="store_true")
     ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the sharded stretch block")
     ap.add_argument("--sharded-steps", type=int, default=6)
@@ -416,6 +417,8 @@ def main():
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
+    if args.ess_budget is None:
+        args.ess_budget = "150,80,130" if world == 1 else "90,50,80"
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
