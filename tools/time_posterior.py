@@ -41,3 +41,17 @@ for opts in ({"cost_order": 0}, {"cost_order": 1}, {"cost_order": 0, "dense_outp
     same = bool(np.array_equal(sv, ref[1]) and (np.array_equal(lp, ref[0]) if not opts.get("dense_output") else np.abs(lp - ref[0])[sv == 0].max() < 1e-9))
     print(json.dumps({"walkers": W, "options": opts, "ms": best, "evals_per_s": W / best * 1e3, "ok_fraction": float((sv == 0).mean()),
                       "same_results_as_first": same}), flush=True)
+# the start ball of the headline bench (65 536 walkers), default options; sha256 of the results for build-to-build comparisons
+import hashlib
+tb = torch.from_numpy(T.gaussian_ball(T.HD_SOL, T.HD_SCALE_VEC, 65536, 1)).cuda()
+lb = torch.empty(65536, dtype=torch.float64, device="cuda"); sb = torch.empty(65536, dtype=torch.int32, device="cuda")
+m.set_option("dense_output", 0); m.set_option("cost_order", 1)
+best = 1e9
+for _ in range(5):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); m.loglik_dev(oh, tb.data_ptr(), 65536, lb.data_ptr(), sb.data_ptr(), s); e1.record()
+    torch.cuda.synchronize(); best = min(best, e0.elapsed_time(e1))
+print(json.dumps({"start_ball_walkers": 65536, "ms": best, "evals_per_s": 65536 / best * 1e3,
+                  "sha256_logp_status": hashlib.sha256(lb.cpu().numpy().tobytes() + sb.cpu().numpy().tobytes()).hexdigest(),
+                  "sha256_posterior_default": hashlib.sha256(ref[0].tobytes() + ref[1].tobytes()).hexdigest()}), flush=True)
+
