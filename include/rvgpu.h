@@ -51,7 +51,7 @@ typedef struct rv_model rv_model; /* parameter schema resident in HBM (state.py:
 #define RV_EL_IY 6
 #define RV_NELEM 7
 #define RV_MAX_PLANETS 5      /* plain likelihood, samplers without derivatives (MH, stretch), WHFast */
-#define RV_MAX_PLANETS_VAR 3  /* value + gradient + Hessian (rv_loglik_d_dd*, SMALA, ALSMALA): error -30 above */
+#define RV_MAX_PLANETS_VAR 5  /* value + gradient + Hessian (rv_loglik_d_dd*, SMALA, ALSMALA): error -30 above */
 
 /* ---- context ---------------------------------------------------------------------------------- */
 int rv_ctx_create(int device, rv_ctx** out);
@@ -119,8 +119,9 @@ int rv_initial_conditions(rv_ctx* ctx, const rv_model* model, const double* thet
 /* ---- State.get_logp_d_dd (state.py:290-294; setup_sim_vars state.py:229-248, get_chi2_d_dd state.py:253-285) ---- */
 /* theta[W][nvars] -> logp[W], grad[W][nvars], hess[W][nvars][nvars] (symmetric), status[W].  The hard prior is tested
  * first (status RV_PRIOR), as the reference's callers do (mcmc.py:171).  On a non-zero status logp = -inf and the
- * walker's grad / hess rows are zero.  Returns -30 when the model has more than RV_MAX_PLANETS_VAR planets or needs more
- * than 448 (set, planet) threads.                                                                                 */
+ * walker's grad / hess rows are zero.  Returns -30 when the model has more than RV_MAX_PLANETS_VAR planets.  Models whose
+ * variational sets do not fit one thread block (three planets with more than 15 free parameters, four and five planets)
+ * run their second-order sets in several launches; the results are those of one launch to rounding.             */
 int rv_loglik_d_dd(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, const double* theta, int64_t W,
                    double* logp, double* grad, double* hess, int32_t* status);
 /* Same with the prior test chosen PER CALL (check_prior = 0: integrate even outside the hard prior, which is what

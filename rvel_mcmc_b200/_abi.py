@@ -15,7 +15,7 @@ import numpy as np
 RV_OK, RV_PRIOR, RV_ENCOUNTER, RV_NONFINITE, RV_NOT_SPD = 0, 1, 3, 8, 9
 ELEMS = ("m", "a", "h", "k", "l", "ix", "iy")       # ABI slot order (RV_EL_*)
 MAX_PLANETS = 5          # RV_MAX_PLANETS (plain likelihood, MH, stretch, WHFast)
-MAX_PLANETS_VAR = 3      # RV_MAX_PLANETS_VAR (gradient + Hessian, SMALA)
+MAX_PLANETS_VAR = 5      # RV_MAX_PLANETS_VAR (gradient + Hessian, SMALA)
 
 
 class RvGpuError(RuntimeError):

@@ -414,10 +414,13 @@ static int var_dev_impl(rv_ctx* ctx, const rv_model* model, const rv_obs* obs, c
     if (model->h.P > rv::MAXP_VAR)
         return fail(ctx, -30, "variational kernel: built for up to %d planets (this model has %d); the plain likelihood, MH and the stretch move take up to %d",
                     rv::MAXP_VAR, model->h.P, rv::MAXP);
+    // models whose (set, planet) threads do not fit one CTA run their second-order sets in chunks (launch_var_chunked); what must
+    // fit is the real + first-order group beside at least one pair -- true for everything the schema allows (5 planets x 7 elements:
+    // 180 threads of 320)
     const bool set_per_lane = model->var_layout == 0 && model->h.P <= 2 && model->h.D == 2 && nv + 1 <= 32;
-    if (!set_per_lane && rv::var_threads_needed(model->h.P, nv) > 448)
-        return fail(ctx, -30, "variational kernel: %d planets x %d free parameters need %d (set, planet) threads; the limit is 448",
-                    model->h.P, nv, rv::var_threads_needed(model->h.P, nv));
+    if (!set_per_lane && !rv::var_model_fits(model->h.P, model->h.D, nv))
+        return fail(ctx, -30, "variational kernel: %d planets x %d free parameters: the real and first-order sets alone need %d threads of one block",
+                    model->h.P, nv, (nv + 1) * model->h.P);
     const int nsets = rv::var_nsets(nv);
     if (int rc = ensure(ctx, &ctx->d_vpart, &ctx->cap_vpart, (size_t)(2 * W) * nsets)) return rc;
     if (int rc = ensure(ctx, &ctx->d_pstat, &ctx->cap_pstat, (size_t)(2 * W))) return rc;

@@ -30,7 +30,7 @@
 namespace rv {
 
 constexpr int MAXP = 5;            // planets per system supported by the compiled plain-likelihood kernels
-constexpr int MAXP_VAR = 3;        // ... by the variational (gradient + Hessian) kernels
+constexpr int MAXP_VAR = 5;        // ... by the variational (gradient + Hessian) kernels
 constexpr int NELEM = 7;           // m, a, h, k, l, ix, iy
 constexpr int MAXV = MAXP * NELEM; // free parameters
 

@@ -37,16 +37,23 @@ RV_HD int round32(int x) { return (x + 31) & ~31; }
 
 // Thread / shared-memory layout of one CTA; identical on host and device.
 struct VarLayout {
-    int P, D, nv, n2, nsets;
+    int P, D, nv, n2, nsets;       // n2 / nsets: the second-order sets / all sets THIS launch carries (see k2_lo)
+    int k2_lo, nsets_total;        // first second-order pair of this launch; sets of the model (the row length of VarArgs::part)
     int base1;     // first thread of the (real + first-order) group; second-order slots start at thread 0
     int need;      // threads that carry a (set, planet)
     int NT;        // threads launched
     int npos;      // doubles per position buffer
     int o_pos, o_vx, o_dm, o_red, o_e, o_hist, total;   // offsets in doubles
 };
-RV_HD VarLayout var_layout(int P, int D, int nv, int NT) {
+// A second-order set depends on the real set and on its two first-order parents only, so a model whose sets do not fit one
+// CTA is integrated in several launches: each carries the real set, all first-order sets and the second-order pairs
+// [k2_lo, k2_lo + k2_n) (k2_n < 0: all of them).  The launches share the step sequence (the step-size controller reads the
+// real particles only); their predictor-corrector iteration counts may differ, i.e. the real trajectory agrees to rounding.
+RV_HD VarLayout var_layout(int P, int D, int nv, int NT, int k2_lo = 0, int k2_n = -1) {
     VarLayout L;
-    L.P = P; L.D = D; L.nv = nv; L.n2 = nv * (nv + 1) / 2; L.nsets = 1 + nv + L.n2;
+    const int n2_all = nv * (nv + 1) / 2;
+    L.P = P; L.D = D; L.nv = nv; L.n2 = (k2_n < 0) ? n2_all : k2_n; L.nsets = 1 + nv + L.n2;
+    L.k2_lo = k2_lo; L.nsets_total = 1 + nv + n2_all;
     L.base1 = round32(L.n2 * P);
     L.need = L.base1 + (nv + 1) * P;
     L.NT = NT;
@@ -62,9 +69,17 @@ RV_HD VarLayout var_layout(int P, int D, int nv, int NT) {
     return L;
 }
 
+// second-order pairs one launch of NT threads can carry beside the real + first-order group (0: the model does not fit)
+RV_HD int var_chunk_pairs(int P, int nv, int NT) {
+    int n = (NT - (nv + 1) * P) / P;
+    while (n > 0 && round32(n * P) + (nv + 1) * P > NT) n--;
+    return n > 0 ? n : 0;
+}
+
 template <int P, int D>
 struct VarThread {
-    int tid, set, planet, order;   // order: 0 real, 1 first, 2 second, -1 idle
+    int tid, set, planet, order;   // order: 0 real, 1 first, 2 second, -1 idle; set: index among the sets of this launch
+    int gset;                      // index among the sets of the model (= set unless the launch carries a chunk of the pairs)
     int sa, sb;                    // parent sets (first-order sets of parameters pa, pb)
     int pa, pb;                    // parameter indices (pa >= pb)
     int ou, oa, ob;                // element offsets of the own / parent sets in a position buffer (set * P * D)
@@ -365,11 +380,13 @@ RV_D bool var_encounter(const double* __restrict__ X0, const VarUniform<P>& u) {
 template <int P, int D>
 RV_D void var_assign(VarThread<P, D>& th, int tid, const VarLayout& L) {
     th.tid = tid;
-    th.order = -1; th.set = 0; th.planet = 0; th.sa = th.sb = 0; th.pa = th.pb = 0;
+    th.order = -1; th.set = 0; th.gset = 0; th.planet = 0; th.sa = th.sb = 0; th.pa = th.pb = 0;
     if (tid < L.n2 * P) {
-        const int k = tid / P;
-        th.planet = tid - k * P;
-        th.set = 1 + L.nv + k;
+        const int kl = tid / P;
+        const int k = L.k2_lo + kl;
+        th.planet = tid - kl * P;
+        th.set = 1 + L.nv + kl;
+        th.gset = 1 + L.nv + k;
         th.order = 2;
         int a = 0;
         while ((a + 1) * (a + 2) / 2 <= k) a++;
@@ -378,6 +395,7 @@ RV_D void var_assign(VarThread<P, D>& th, int tid, const VarLayout& L) {
     } else if (tid >= L.base1 && tid < L.need) {
         const int q = tid - L.base1;
         th.set = q / P;
+        th.gset = th.set;
         th.planet = q - th.set * P;
         th.order = th.set == 0 ? 0 : 1;
         th.pa = th.pb = th.set == 0 ? 0 : th.set - 1;
@@ -754,8 +772,10 @@ RV_D void var_run_items(Exec& ex, const VarArgs& a, const VarLayout& L, double* 
         // ---- results of this leg -----------------------------------------------------------------
         const int fs = final_status;
         ex.each([&](VarThread<P, D>& th) {
-            if (th.tid == 0) a.part_status[item] = fs;
-            if (fs == ST_OK && th.order >= 0 && th.planet == 0) a.part[item * L.nsets + th.set] = th.acc;
+            if (th.tid == 0 && (L.k2_lo == 0 || fs != ST_OK)) a.part_status[item] = fs;     // a failure in any launch fails the leg
+            // value and gradient come from the launch that carries the first pairs
+            if (fs == ST_OK && th.order >= 0 && th.planet == 0 && (th.order == 2 || L.k2_lo == 0))
+                a.part[item * L.nsets_total + th.gset] = th.acc;
         });
         ex.add_work(a.work_counters, n_force, n_attempt);
     }

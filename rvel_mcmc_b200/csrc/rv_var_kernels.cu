@@ -204,9 +204,9 @@ __global__ void var_finalize_kernel(const double* __restrict__ part, const int* 
 }
 
 template <int P, int D, int NT, int MINB>
-static cudaError_t launch_var_one(const VarArgs& a, int nv, int num_sms, cudaStream_t stream) {
+static cudaError_t launch_var_one(const VarArgs& a, int nv, int num_sms, cudaStream_t stream, int k2_lo = 0, int k2_n = -1) {
     auto kern = var_kernel<P, D, NT, MINB>;
-    const VarLayout L = var_layout(P, D, nv, NT);
+    const VarLayout L = var_layout(P, D, nv, NT, k2_lo, k2_n);
     if (L.need > NT) return cudaErrorInvalidConfiguration;
     const size_t smem = sizeof(double) * (size_t)L.total;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -220,6 +220,32 @@ static cudaError_t launch_var_one(const VarArgs& a, int nv, int num_sms, cudaStr
     if (blocks < 1) blocks = 1;
     kern<<<(unsigned)blocks, NT, smem, stream>>>(a, L);
     return cudaGetLastError();
+}
+
+// Models whose sets do not fit one CTA: several launches, each with the real set, the first-order sets and a chunk of the
+// second-order pairs (var_layout).  The work-queue counter is reset between the launches (the finalize kernel resets it
+// after the last one).
+template <int P, int D, int NT>
+static cudaError_t launch_var_chunked(const VarArgs& a, int nv, int num_sms, cudaStream_t stream) {
+    const int n2 = nv * (nv + 1) / 2, chunk = var_chunk_pairs(P, nv, NT);
+    if (chunk < 1) return cudaErrorInvalidConfiguration;
+    for (int lo = 0; lo < n2 || lo == 0; lo += chunk) {
+        if (lo > 0) {
+            cudaError_t e = cudaMemsetAsync(a.item_counter, 0, sizeof(unsigned long long), stream);
+            if (e != cudaSuccess) return e;
+        }
+        const int n = (n2 - lo < chunk) ? n2 - lo : chunk;
+        cudaError_t e = launch_var_one<P, D, NT, 1>(a, nv, num_sms, stream, lo, n);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+// 1 when launch_var has a configuration for the thread-per-(set, planet) layout of this model (one launch or chunks)
+int var_model_fits(int P, int D, int nv) {
+    if (P < 1 || P > MAXP_VAR) return 0;
+    if (P <= 2) return 1;                                    // at most 14 free parameters: always one launch
+    return var_chunk_pairs(P, nv, D == 3 ? 320 : 448) >= 1 || nv == 0;
 }
 
 // threads needed by a model (host-side check shared with the ABI)
@@ -252,7 +278,15 @@ cudaError_t launch_var(const VarArgs& a, int P, int D, int nv, int layout, int n
     if (P == 2 && D == 2 && need <= 160) return launch_var_one<2, 2, 160, 3>(a, nv, num_sms, stream);
     if (P == 2 && D == 3 && need <= 256) return launch_var_one<2, 3, 256, 1>(a, nv, num_sms, stream);
     if (P == 3 && D == 2 && need <= 448) return launch_var_one<3, 2, 448, 1>(a, nv, num_sms, stream);
-    if (P == 3 && D == 3 && need <= 448) return launch_var_one<3, 3, 448, 1>(a, nv, num_sms, stream);
+    // (inclined models: 320 threads -- the per-thread shared-memory history, 21 D doubles, is what fills the SM's 227 KB)
+    if (P == 3 && D == 3 && need <= 320) return launch_var_one<3, 3, 320, 1>(a, nv, num_sms, stream);
+    // everything else the schema allows (state.py:8-31 is open-ended): the second-order sets in chunks of what one CTA holds
+    if (P == 3 && D == 2) return launch_var_chunked<3, 2, 448>(a, nv, num_sms, stream);
+    if (P == 3 && D == 3) return launch_var_chunked<3, 3, 320>(a, nv, num_sms, stream);
+    if (P == 4 && D == 2) return launch_var_chunked<4, 2, 448>(a, nv, num_sms, stream);
+    if (P == 4 && D == 3) return launch_var_chunked<4, 3, 320>(a, nv, num_sms, stream);
+    if (P == 5 && D == 2) return launch_var_chunked<5, 2, 448>(a, nv, num_sms, stream);
+    if (P == 5 && D == 3) return launch_var_chunked<5, 3, 320>(a, nv, num_sms, stream);
     return cudaErrorInvalidConfiguration;
 }
 

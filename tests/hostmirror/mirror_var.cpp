@@ -22,16 +22,33 @@ struct HostVarExec {
     void add_work(unsigned long long* wc, unsigned long long nf, unsigned long long na) { if (wc) { wc[0] += nf; wc[1] += na; } }
 };
 
+int g_var_nt_cap = 0;       // > 0: threads of one emulated CTA; models that need more run in chunks of second-order pairs
+
 template <int P, int D>
-int run(const rv::VarArgs& a, int nv) {
-    int NT = 64;
-    rv::VarLayout L = rv::var_layout(P, D, nv, NT);
-    while (L.need > NT) { NT += 32; L = rv::var_layout(P, D, nv, NT); }
+int run_launch(const rv::VarArgs& a, const rv::VarLayout& L, int NT) {
     std::vector<double> sm((size_t)L.total, 0.0);
     HostVarExec<P, D> ex;
     ex.th.resize(NT);
     for (int t = 0; t < NT; t++) rv::var_assign(ex.th[t], t, L);
     rv::var_run_items<P, D>(ex, a, L, sm.data());
+    return 0;
+}
+
+template <int P, int D>
+int run(const rv::VarArgs& a, int nv) {
+    int NT = 64;
+    rv::VarLayout L = rv::var_layout(P, D, nv, NT);
+    while (L.need > NT) { NT += 32; L = rv::var_layout(P, D, nv, NT); }
+    if (g_var_nt_cap <= 0 || L.need <= g_var_nt_cap) return run_launch<P, D>(a, L, NT);
+    // the launcher's chunked schedule (launch_var_chunked in rv_var_kernels.cu)
+    NT = g_var_nt_cap;
+    const int n2 = nv * (nv + 1) / 2, chunk = rv::var_chunk_pairs(P, nv, NT);
+    if (chunk < 1) return -30;
+    for (int lo = 0; lo < n2; lo += chunk) {
+        *a.item_counter = 0;
+        const int n = (n2 - lo < chunk) ? n2 - lo : chunk;
+        run_launch<P, D>(a, rv::var_layout(P, D, nv, NT, lo, n), NT);
+    }
     return 0;
 }
 // the set-per-lane layout (rv_var2.cuh): barriers and named-barrier signals are no-ops in a sequential run because
@@ -66,6 +83,7 @@ int run2(const rv::VarArgs& a, int nv) {
 
 static int g_var_layout = 0;      // 0: thread per (set, planet) (rv_var.cuh); 2: lane per set (rv_var2.cuh)
 extern "C" void mirror_set_var_layout(int v) { g_var_layout = v; }
+extern "C" void mirror_set_var_nt_cap(int v) { g_var_nt_cap = v; }
 
 extern "C" int mirror_loglik_d_dd(int P, const double* fixed, int nvars, const int* fp, const int* fe, double hill, int dims,
                                   const double* tf, const double* rvf, const double* ef, int nf,
@@ -99,6 +117,10 @@ extern "C" int mirror_loglik_d_dd(int P, const double* fixed, int nvars, const i
         case 23: run<2, 3>(a, nvars); break;
         case 32: run<3, 2>(a, nvars); break;
         case 33: run<3, 3>(a, nvars); break;
+        case 42: run<4, 2>(a, nvars); break;
+        case 43: run<4, 3>(a, nvars); break;
+        case 52: run<5, 2>(a, nvars); break;
+        case 53: run<5, 3>(a, nvars); break;
         default: return -9;
     }
     for (long long w = 0; w < W; w++) {

@@ -107,16 +107,30 @@ def test_other_shapes(ctx, planets, free):
         assert np.abs(hg[w] - ho[w]).max() <= 1e-6 * np.abs(ho[w]).max()
 
 
-def test_model_too_large_is_an_error(ctx):
-    from rvel_mcmc_b200 import _abi
-    planets = [{"m": 1e-3, "a": 0.3 + 0.2 * i, "h": 0.0, "k": 0.0, "l": 0.5 * i, "ix": 0.01, "iy": 0.0} for i in range(3)]
+def test_three_planets_all_elements_runs_in_chunks(ctx):
+    """3 planets x 7 free elements = 21 parameters: 253 variational sets x 3 planets = 759 (set, planet) threads do not fit one
+    thread block (448); the second-order sets run in two launches (launch_var_chunked).  Round 1 refused this model (-30)."""
+    planets = [{"m": 1e-3, "a": 0.3 + 0.2 * i, "h": 0.01 * i, "k": 0.02, "l": 0.5 * i, "ix": 0.01, "iy": 0.005 * i} for i in range(3)]
     E = T.elems_from_planets(planets)
     fp = [i for i in range(3) for _ in range(7)]
     fe = list(range(7)) * 3
-    obs = T.load_vels("HD155358.vels")
+    rng = np.random.RandomState(5)
+    obs = T.Obs()
+    obs.tf = np.concatenate([[0.0], np.sort(rng.uniform(0, 3.0, 10))])
+    obs.tb = np.sort(rng.uniform(-3.0, 0, 10))
+    obs.rvf = 1e-4 * rng.normal(size=11); obs.rvb = 1e-4 * rng.normal(size=10)
+    obs.errorf = np.full(11, 2e-4); obs.errorb = np.full(10, 2e-4)
+    obs.Npoints = 20
     oh, m = _handles(ctx, obs, E, fp, fe, 1.0)
-    with pytest.raises(_abi.RvGpuError):
-        m.loglik_d_dd(oh, np.array([E.reshape(-1)]))
+    theta = np.array([E.reshape(-1)]) * (1 + 1e-4 * rng.normal(size=(3, 21)))
+    lg, gg, hg, sg = m.loglik_d_dd(oh, theta)
+    lo, go, ho, so, _ = T.orc_logp_d_dd_batch(E, fp, fe, 1.0, obs, theta)
+    assert np.array_equal(sg, so) and (so == 0).all()
+    assert np.abs(lg - lo).max() < 1e-6 * max(1.0, np.abs(lo).max())
+    for w in range(3):
+        assert np.abs(gg[w] - go[w]).max() <= 1e-6 * np.abs(go[w]).max()
+        assert np.abs(hg[w] - ho[w]).max() <= 1e-6 * np.abs(ho[w]).max()
+        assert np.array_equal(hg[w], hg[w].T)
 
 
 def test_state_api_get_logp_d_dd():

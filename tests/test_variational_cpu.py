@@ -134,3 +134,41 @@ def test_block_emulation_other_shapes(planets, free, var_layout):
     assert abs(lm[0] - lo[0]) < 1e-9 * max(1.0, abs(lo[0]))
     assert np.abs(gm - go).max() <= 1e-7 * np.abs(go).max()
     assert np.abs(hm - ho).max() <= 1e-7 * np.abs(ho).max()
+
+
+def test_chunked_second_order_sets_equal_one_launch():
+    """Models whose (set, planet) threads do not fit one CTA run their second-order pairs in several launches
+    (launch_var_chunked): emulated here with a 64-thread cap on HD155358 (66 sets x 2 planets -> four launches); value and
+    gradient identical, Hessian to rounding (the launches' predictor-corrector iteration counts may differ)."""
+    obs = _hd()
+    theta = T.gaussian_ball(T.HD_SOL, T.HD_SCALE_VEC, 2, 5)
+    lib = T.mirror()
+    lib.mirror_set_var_layout(0)
+    l0, g0, h0, s0, c0 = T.mirror_loglik_d_dd(Z2, T.FP10, T.FE10, 2.0, obs, theta)
+    lib.mirror_set_var_nt_cap(64)
+    try:
+        l1, g1, h1, s1, c1 = T.mirror_loglik_d_dd(Z2, T.FP10, T.FE10, 2.0, obs, theta)
+    finally:
+        lib.mirror_set_var_nt_cap(0)
+    assert np.array_equal(s0, s1) and (s0 == 0).all()
+    assert c1[1] == 4 * c0[1]                   # four launches, same step sequence in each
+    assert np.array_equal(l0, l1) and np.array_equal(g0, g1)
+    assert np.abs(h1 - h0).max() <= 1e-12 * np.abs(h0).max()
+
+
+def test_four_planets_in_chunks_match_oracle():
+    """Four planets, 20 free parameters (231 sets x 4 planets = 924 threads against 448 per CTA): three launches."""
+    obs, fixed, fp, fe, center, sc = T.many_planet_problem(4, nper=6, tmax=6.0)
+    theta = center[None, :]
+    lo, go, ho, so, _ = T.orc_logp_d_dd_batch(fixed, fp, fe, 2.0, obs, theta)
+    lib = T.mirror()
+    lib.mirror_set_var_layout(0)
+    lib.mirror_set_var_nt_cap(448)
+    try:
+        lm, gm, hm, sm, _ = T.mirror_loglik_d_dd(fixed, fp, fe, 2.0, obs, theta)
+    finally:
+        lib.mirror_set_var_nt_cap(0)
+    assert so[0] == 0 and sm[0] == 0
+    assert abs(lm[0] - lo[0]) < 1e-9
+    assert np.abs(gm[0] - go[0]).max() <= 1e-8 * np.abs(go[0]).max()
+    assert np.abs(hm[0] - ho[0]).max() <= 1e-8 * np.abs(ho[0]).max()
